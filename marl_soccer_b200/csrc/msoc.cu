@@ -1,0 +1,597 @@
+/*
+ * msoc.cu -- B200 (sm_100a) kernels and the C-ABI (include/msoc.h) of the batched 2v2 soccer
+ * simulator.  Replaces the reference's per-env Python/pymunk update loop
+ * (soccer_simulation/marl_vecenv.py:30-68 -> soccer_env.py:100-154 -> game/game.py:378-437 ->
+ * pymunk Space.step) with ONE fused kernel per vectorised step.
+ *
+ * Data layout: struct-of-arrays over N envs, float4-packed (msoc::Arrays in step_core.cuh); one
+ * thread owns one env, one warp owns a tile of 32 consecutive envs.  State loads/stores are
+ * 16 B per lane, fully coalesced.  Observations (N,4,66) are written per warp tile: the new 22-float
+ * frames are staged through shared memory and the 3-frame stack is shifted with coalesced 8-byte
+ * accesses (rows of 264 B are 8-byte aligned), so every DRAM sector is fully used.
+ *
+ * There is no CPU fallback in this library: every entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/msoc.h"
+#include "step_core.cuh"
+
+using namespace msoc;
+
+/* ------------------------------------------------------------------------------------ errors */
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char *what, cudaError_t ce = cudaSuccess)
+{
+    char buf[512];
+    if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_last_error = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return fail(MSOC_ERR_CUDA, #expr, _e);         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+/* ------------------------------------------------------------------------------------ handle */
+struct msoc_handle {
+    int device;
+    int64_t n;
+    uint64_t global_offset;
+    SimCfg cfg;
+    Arrays A;
+    int cur; /* which half of the ping-pong arbiter cache is current */
+    void *slab;
+    /* internal I/O buffers of the host-buffer API */
+    float *d_obs, *d_act, *d_rew;
+    uint8_t *d_done, *d_mask;
+    int8_t *d_goal;
+    int32_t *d_score;
+    double *d_stats; /* 8 doubles, msoc_stats layout */
+    void *d_stage; size_t stage_bytes; /* get/set_state staging */
+};
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int BLOCK = WARPS_PER_BLOCK * 32;
+constexpr int ENV_STRIDE = 89; /* floats of shared memory per env for the 4 new frames (odd: no bank conflicts) */
+
+/* ------------------------------------------------------------------ coalesced observation tile */
+/* One warp writes the stacked observations of its 32 envs (33 792 contiguous bytes).  Row r = env*4 +
+   agent holds 33 float2: [frame t-2 | frame t-1 | frame t].  Frames t-2, t-1 come from obs_in shifted
+   by one frame (soccer_env.py:134-137), frame t from shared memory; envs in fresh_mask (reset or
+   auto-reset, soccer_env.py:92-96) get three copies of the new frame.  Safe when obs_out == obs_in:
+   within a batch of rows all loads precede all stores. */
+__device__ __forceinline__ void write_obs_tile(const float *obs_in, float *obs_out, const float *s_new,
+                                               uint32_t write_mask, uint32_t fresh_mask, int64_t env_base, int lane)
+{
+    const int f_lane = lane / 11, j_lane = lane - f_lane * 11;
+    const float2 *in2 = reinterpret_cast<const float2 *>(obs_in) + env_base * 132;
+    float2 *out2 = reinterpret_cast<float2 *>(obs_out) + env_base * 132;
+    constexpr int RB = 8;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 128; r0 += RB) {
+        float2 v[RB];
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int r = r0 + u, e = r >> 2, a = r & 3;
+            if (!((write_mask >> e) & 1u)) continue;
+            if (f_lane == 2 || ((fresh_mask >> e) & 1u)) {
+                const float *s = s_new + e * ENV_STRIDE + a * 22 + 2 * j_lane;
+                v[u] = make_float2(s[0], s[1]);
+            } else {
+                v[u] = in2[r * 33 + lane + 11];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < RB; u++) {
+            const int r = r0 + u, e = r >> 2;
+            if ((write_mask >> e) & 1u) out2[r * 33 + lane] = v[u];
+        }
+    }
+    /* last float2 of every row (frame t, floats 20-21) */
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = lane + 32 * i, e = r >> 2, a = r & 3;
+        if ((write_mask >> e) & 1u) {
+            const float *s = s_new + e * ENV_STRIDE + a * 22 + 20;
+            out2[r * 33 + 32] = make_float2(s[0], s[1]);
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------- the fused step */
+struct StepParams {
+    Arrays A;
+    SimCfg cfg;
+    const float *actions; /* (N,4,3) */
+    const float *obs_in;  /* (N,4,66) */
+    float *obs_out;       /* (N,4,66) */
+    float *reward;        /* (N,2) */
+    uint8_t *done;        /* (N) */
+    int8_t *goal;         /* (N) */
+    int32_t *score;       /* (N,2) or null */
+    double *stats;        /* 8 */
+    uint64_t global_offset;
+    uint32_t flags;
+    int cur;
+};
+
+__global__ void __launch_bounds__(BLOCK, 4) msoc_step_kernel(const __grid_constant__ StepParams P)
+{
+    __shared__ float s_frames[WARPS_PER_BLOCK][32 * ENV_STRIDE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t env_base = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 32;
+    const int64_t e = env_base + lane;
+    const bool active = e < P.A.n;
+    if (env_base >= P.A.n) return; /* whole warp out of range */
+
+    StepOut out;
+    out.reward = 0.0f; out.done = 0; out.goal = 0; out.fresh_episode = false; out.finished_return = 0.0f;
+    out.n_contacts = 0; out.overflow = 0; out.score_b = 0; out.score_r = 0;
+    if (active) {
+        float act[12];
+        const float4 *a4 = reinterpret_cast<const float4 *>(P.actions + e * 12);
+        const float4 x0 = __ldg(a4), x1 = __ldg(a4 + 1), x2 = __ldg(a4 + 2);
+        act[0] = x0.x; act[1] = x0.y; act[2] = x0.z; act[3] = x0.w;
+        act[4] = x1.x; act[5] = x1.y; act[6] = x1.z; act[7] = x1.w;
+        act[8] = x2.x; act[9] = x2.y; act[10] = x2.z; act[11] = x2.w;
+        Env E;
+        load_env(P.A, e, E);
+        env_step<22>(E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags,
+                     &s_frames[warp][lane * ENV_STRIDE], out);
+        store_env(P.A, e, E);
+        reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
+        P.done[e] = out.done;
+        P.goal[e] = out.goal;
+        if (P.score != nullptr) reinterpret_cast<int2 *>(P.score)[e] = make_int2(out.score_b, out.score_r);
+    }
+    const uint32_t write_mask = __ballot_sync(0xffffffffu, active);
+    const uint32_t fresh_mask = __ballot_sync(0xffffffffu, active && out.fresh_episode);
+    __syncwarp();
+    write_obs_tile(P.obs_in, P.obs_out, s_frames[warp], write_mask, fresh_mask, env_base, lane);
+
+    /* per-rollout statistics (marl-soccer.ipynb:411-429): warp reduce, one atomic per warp and counter */
+    const uint32_t done_mask = __ballot_sync(0xffffffffu, out.done != 0);
+    const uint32_t gb_mask = __ballot_sync(0xffffffffu, out.goal > 0);
+    const uint32_t gr_mask = __ballot_sync(0xffffffffu, out.goal < 0);
+    int nc = out.n_contacts, ov = out.overflow;
+    float ret = out.finished_return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nc += __shfl_xor_sync(0xffffffffu, nc, o);
+        ov += __shfl_xor_sync(0xffffffffu, ov, o);
+        ret += __shfl_xor_sync(0xffffffffu, ret, o);
+    }
+    if (lane == 0) {
+        if (done_mask) { atomicAdd(P.stats + 0, (double)__popc(done_mask)); atomicAdd(P.stats + 1, (double)ret); }
+        if (gb_mask) atomicAdd(P.stats + 2, (double)__popc(gb_mask));
+        if (gr_mask) atomicAdd(P.stats + 3, (double)__popc(gr_mask));
+        atomicAdd(P.stats + 4, (double)__popc(write_mask));
+        if (nc) atomicAdd(P.stats + 5, (double)nc);
+        if (ov) atomicAdd(P.stats + 6, (double)ov);
+    }
+}
+
+/* ------------------------------------------------------------------------------------- reset */
+struct ResetParams {
+    Arrays A;
+    SimCfg cfg;
+    const uint8_t *mask; /* N or null */
+    float *obs_out;      /* (N,4,66) or null */
+    uint64_t global_offset, seed;
+    int mode, has_seed, cur;
+};
+
+__global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant__ ResetParams P)
+{
+    __shared__ float s_frames[WARPS_PER_BLOCK][32 * ENV_STRIDE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t env_base = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 32;
+    const int64_t e = env_base + lane;
+    if (env_base >= P.A.n) return;
+    const bool doit = (e < P.A.n) && (P.mask == nullptr || P.mask[e] != 0);
+    if (doit) {
+        const uint64_t gidx = P.global_offset + (uint64_t)e;
+        uint64_t seed; uint32_t sc;
+        if (P.has_seed) { seed = P.seed + gidx; sc = 0; P.A.seed[e] = seed; } /* marl_vecenv.py:23: seed + i */
+        else { seed = P.A.seed[e]; sc = P.A.spawn_count[e]; }
+        Env E;
+        env_full_reset(E, P.mode, seed, gidx, sc);
+        P.A.spawn_count[e] = sc;
+        store_env(P.A, e, E);
+        make_frames<22>(E, P.cfg, &s_frames[warp][lane * ENV_STRIDE]);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, doit);
+    __syncwarp();
+    if (P.obs_out != nullptr && m != 0u) write_obs_tile(P.obs_out, P.obs_out, s_frames[warp], m, m, env_base, lane);
+}
+
+/* -------------------------------------------------------------------- state inject / extract */
+__global__ void msoc_get_state_kernel(Arrays A, int cur, const int64_t *idx, int64_t n, msoc_env_state *out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t e = idx[t];
+    Env E;
+    load_env(A, e, E);
+    msoc_env_state S;
+    memset(&S, 0, sizeof S);
+    for (int i = 0; i < 5; i++) {
+        S.pos[i][0] = E.px[i]; S.pos[i][1] = E.py[i]; S.vel[i][0] = E.vx[i]; S.vel[i][1] = E.vy[i];
+        S.angvel[i] = E.w[i]; S.vbias[i][0] = E.vbx[i]; S.vbias[i][1] = E.vby[i];
+    }
+    for (int i = 0; i < 4; i++) { S.ang[i] = E.ang[i]; S.wbias[i] = E.wb[i]; }
+    S.ep_return = E.ep_return; S.steps = E.steps; S.score[0] = E.score_b; S.score[1] = E.score_r;
+    S.mode = (int)((E.flags & FLAG_MODE_MASK) >> FLAG_MODE_SHIFT);
+    S.spawn_count = A.spawn_count[e]; S.seed = A.seed[e];
+    const uint32_t cnt = E.flags & FLAG_CACHE_MASK;
+    S.cache_count = cnt;
+    for (uint32_t j = 0; j < cnt; j++) {
+        S.cache_info[j] = A.cache_info[cur][(int64_t)j * A.n + e];
+        S.cache_jn[j] = A.cache_jn[cur][(int64_t)j * A.n + e];
+        S.cache_jt[j] = A.cache_jt[cur][(int64_t)j * A.n + e];
+    }
+    out[t] = S;
+}
+
+__global__ void msoc_set_state_kernel(Arrays A, int cur, const int64_t *idx, int64_t n, const msoc_env_state *in)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t e = idx[t];
+    const msoc_env_state &S = in[t];
+    Env E;
+    for (int i = 0; i < 5; i++) {
+        E.px[i] = S.pos[i][0]; E.py[i] = S.pos[i][1]; E.vx[i] = S.vel[i][0]; E.vy[i] = S.vel[i][1];
+        E.w[i] = S.angvel[i]; E.vbx[i] = S.vbias[i][0]; E.vby[i] = S.vbias[i][1];
+    }
+    for (int i = 0; i < 4; i++) { E.ang[i] = S.ang[i]; E.wb[i] = S.wbias[i]; }
+    E.ep_return = S.ep_return; E.steps = S.steps; E.score_b = S.score[0]; E.score_r = S.score[1];
+    uint32_t cnt = S.cache_count > (uint32_t)MAX_CACHE ? (uint32_t)MAX_CACHE : S.cache_count;
+    E.flags = cnt | (((uint32_t)S.mode & 3u) << FLAG_MODE_SHIFT);
+    A.spawn_count[e] = S.spawn_count; A.seed[e] = S.seed;
+    for (uint32_t j = 0; j < cnt; j++) {
+        A.cache_info[cur][(int64_t)j * A.n + e] = S.cache_info[j];
+        A.cache_jn[cur][(int64_t)j * A.n + e] = S.cache_jn[j];
+        A.cache_jt[cur][(int64_t)j * A.n + e] = S.cache_jt[j];
+    }
+    store_env(A, e, E);
+}
+
+__global__ void msoc_init_kernel(Arrays A, uint64_t seed)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.n) return;
+    A.seed[e] = seed;
+    A.spawn_count[e] = 0;
+}
+
+/* ---------------------------------------------------------------------------------- C-ABI */
+extern "C" {
+
+const char *msoc_last_error(void) { return g_last_error.c_str(); }
+int msoc_version(void) { return MSOC_VERSION; }
+uint64_t msoc_launch_count(void) { return g_launches.load(); }
+int64_t msoc_num_envs(const msoc_handle *h) { return h ? h->n : 0; }
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int grid_for(int64_t n) { return (int)((n + BLOCK - 1) / BLOCK); }
+
+static void fill_cfg(const msoc_config *c, SimCfg &s)
+{
+    s.max_velocity = c->max_velocity;
+    s.agent_minv = 1.0f / c->agent_mass; s.ball_minv = 1.0f / c->ball_mass;
+    s.agent_iinv = 1.0f / c->agent_moment; s.ball_iinv = 1.0f / c->ball_moment;
+    s.agent_friction = c->agent_friction; s.ball_friction = c->ball_friction;
+    s.force_max = c->action_force_max; s.torque_max = c->action_torque_max;
+    s.max_ang_vel = c->max_angular_velocity;
+    s.prox_mult = c->ball_proximity_multiplier; s.move_mult = c->move_ball_to_goal_multiplier;
+    s.goal_reward = c->goal_scored_reward; s.conceded_penalty = c->goal_conceded_penalty;
+    s.alive_penalty = c->alive_penalty; s.score_diff_mult = c->score_difference_multiplier;
+    s.max_steps = c->max_steps; s.pad = 0;
+}
+
+int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, uint64_t seed, float *d_obs_out, void *stream);
+
+int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t seed, uint64_t global_env_offset,
+                msoc_handle **out)
+{
+    if (!cfg || !out || n_envs <= 0) return fail(MSOC_ERR_INVALID, "msoc_create: bad argument");
+    if (!(cfg->agent_mass > 0.0f) || !(cfg->ball_mass > 0.0f) || !(cfg->agent_moment > 0.0f) || !(cfg->ball_moment > 0.0f))
+        return fail(MSOC_ERR_INVALID, "msoc_create: masses and moments must be positive");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        return fail(MSOC_ERR_CUDA, "msoc_create: no CUDA device (this library has no CPU fallback)", ce);
+    if (device < 0 || device >= ndev) return fail(MSOC_ERR_INVALID, "msoc_create: bad device index");
+    DeviceGuard guard(device);
+
+    msoc_handle *h = new msoc_handle();
+    memset(h, 0, sizeof *h);
+    h->device = device; h->n = n_envs; h->global_offset = global_env_offset; h->cur = 0;
+    fill_cfg(cfg, h->cfg);
+
+    const size_t n = (size_t)n_envs;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    size_t o_body[5];
+    for (int i = 0; i < 5; i++) o_body[i] = take(n * sizeof(float4));
+    const size_t o_ang = take(n * sizeof(float4)), o_w = take(n * sizeof(float4));
+    const size_t o_bw = take(n * sizeof(float2)), o_cnt = take(n * sizeof(int4));
+    const size_t o_vb01 = take(n * sizeof(float4)), o_vb23 = take(n * sizeof(float4)), o_vb4w = take(n * sizeof(float4));
+    const size_t o_wb23 = take(n * sizeof(float2));
+    const size_t o_seed = take(n * sizeof(uint64_t)), o_sc = take(n * sizeof(uint32_t));
+    size_t o_ci[2], o_cjn[2], o_cjt[2];
+    for (int k = 0; k < 2; k++) {
+        o_ci[k] = take(n * MAX_CACHE * sizeof(uint32_t));
+        o_cjn[k] = take(n * MAX_CACHE * sizeof(float));
+        o_cjt[k] = take(n * MAX_CACHE * sizeof(float));
+    }
+    const size_t o_obs = take(n * 4 * OBS * sizeof(float)), o_act = take(n * 12 * sizeof(float));
+    const size_t o_rew = take(n * 2 * sizeof(float)), o_done = take(n), o_goal = take(n), o_mask = take(n);
+    const size_t o_score = take(n * 2 * sizeof(int32_t));
+    const size_t o_stats = take(8 * sizeof(double));
+    const size_t total = off;
+
+    ce = cudaMalloc(&h->slab, total);
+    if (ce != cudaSuccess) { delete h; return fail(MSOC_ERR_ALLOC, "msoc_create: cudaMalloc", ce); }
+    ce = cudaMemset(h->slab, 0, total);
+    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: cudaMemset", ce); }
+    char *base = (char *)h->slab;
+    Arrays &A = h->A;
+    A.n = n_envs;
+    for (int i = 0; i < 5; i++) A.body[i] = (float4 *)(base + o_body[i]);
+    A.ang = (float4 *)(base + o_ang); A.angvel = (float4 *)(base + o_w);
+    A.ballw_ret = (float2 *)(base + o_bw); A.counters = (int4 *)(base + o_cnt);
+    A.vb01 = (float4 *)(base + o_vb01); A.vb23 = (float4 *)(base + o_vb23); A.vb4w = (float4 *)(base + o_vb4w);
+    A.wb23 = (float2 *)(base + o_wb23);
+    A.seed = (uint64_t *)(base + o_seed); A.spawn_count = (uint32_t *)(base + o_sc);
+    for (int k = 0; k < 2; k++) {
+        A.cache_info[k] = (uint32_t *)(base + o_ci[k]);
+        A.cache_jn[k] = (float *)(base + o_cjn[k]);
+        A.cache_jt[k] = (float *)(base + o_cjt[k]);
+    }
+    h->d_obs = (float *)(base + o_obs); h->d_act = (float *)(base + o_act); h->d_rew = (float *)(base + o_rew);
+    h->d_done = (uint8_t *)(base + o_done); h->d_goal = (int8_t *)(base + o_goal); h->d_mask = (uint8_t *)(base + o_mask);
+    h->d_score = (int32_t *)(base + o_score);
+    h->d_stats = (double *)(base + o_stats);
+
+    msoc_init_kernel<<<(unsigned)((n_envs + 255) / 256), 256>>>(A, seed);
+    g_launches++;
+    /* Game.__init__ -> setup_field -> reset(): first spawn in the default random mode */
+    int rc = msoc_reset(h, nullptr, MSOC_MODE_RANDOM, 0, 0, h->d_obs, nullptr);
+    if (rc != MSOC_OK) { cudaFree(h->slab); delete h; return rc; }
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: init", ce); }
+    *out = h;
+    return MSOC_OK;
+}
+
+int msoc_destroy(msoc_handle *h)
+{
+    if (!h) return MSOC_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    if (h->d_stage) cudaFree(h->d_stage);
+    cudaFree(h->slab);
+    delete h;
+    return MSOC_OK;
+}
+
+int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, uint64_t seed, float *d_obs_out, void *stream)
+{
+    if (!h) return fail(MSOC_ERR_INVALID, "msoc_reset: null handle");
+    if (mode < 0 || mode > 2) return fail(MSOC_ERR_INVALID, "msoc_reset: bad mode");
+    DeviceGuard guard(h->device);
+    ResetParams P;
+    P.A = h->A; P.cfg = h->cfg; P.mask = d_mask; P.obs_out = d_obs_out;
+    P.global_offset = h->global_offset; P.seed = seed; P.mode = mode; P.has_seed = has_seed; P.cur = h->cur;
+    msoc_reset_kernel<<<grid_for(h->n), BLOCK, 0, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return MSOC_OK;
+}
+
+int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, float *d_obs_out, float *d_reward,
+              uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags, void *stream)
+{
+    if (!h || !d_actions || !d_obs_in || !d_obs_out || !d_reward || !d_done || !d_goal)
+        return fail(MSOC_ERR_INVALID, "msoc_step: null argument");
+    DeviceGuard guard(h->device);
+    StepParams P;
+    P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_in = d_obs_in; P.obs_out = d_obs_out;
+    P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
+    P.global_offset = h->global_offset; P.flags = flags; P.cur = h->cur;
+    msoc_step_kernel<<<grid_for(h->n), BLOCK, 0, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    h->cur ^= 1;
+    CUDA_TRY(cudaGetLastError());
+    return MSOC_OK;
+}
+
+int msoc_step_host(msoc_handle *h, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done,
+                   int8_t *h_goal, int32_t *h_score, uint32_t flags, void *stream)
+{
+    if (!h || !h_actions) return fail(MSOC_ERR_INVALID, "msoc_step_host: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->n;
+    CUDA_TRY(cudaMemcpyAsync(h->d_act, h_actions, n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = msoc_step(h, h->d_act, h->d_obs, h->d_obs, h->d_rew, h->d_done, h->d_goal, h->d_score, flags, stream);
+    if (rc != MSOC_OK) return rc;
+    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, n * 4 * OBS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_rew, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    if (h_goal) CUDA_TRY(cudaMemcpyAsync(h_goal, h->d_goal, n, cudaMemcpyDeviceToHost, st));
+    if (h_score) CUDA_TRY(cudaMemcpyAsync(h_score, h->d_score, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MSOC_OK;
+}
+
+int msoc_reset_host(msoc_handle *h, const uint8_t *h_mask, int mode, int has_seed, uint64_t seed, float *h_obs, void *stream)
+{
+    if (!h) return fail(MSOC_ERR_INVALID, "msoc_reset_host: null handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->n;
+    if (h_mask) CUDA_TRY(cudaMemcpyAsync(h->d_mask, h_mask, n, cudaMemcpyHostToDevice, st));
+    int rc = msoc_reset(h, h_mask ? h->d_mask : nullptr, mode, has_seed, seed, h->d_obs, stream);
+    if (rc != MSOC_OK) return rc;
+    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, n * 4 * OBS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MSOC_OK;
+}
+
+int msoc_read_counters(msoc_handle *h, int32_t *h_score, int32_t *h_steps, void *stream)
+{
+    if (!h) return fail(MSOC_ERR_INVALID, "msoc_read_counters: null handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int4> tmp((size_t)h->n);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->A.counters, (size_t)h->n * sizeof(int4), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < h->n; i++) {
+        if (h_steps) h_steps[i] = tmp[(size_t)i].x;
+        if (h_score) { h_score[2 * i] = tmp[(size_t)i].y; h_score[2 * i + 1] = tmp[(size_t)i].z; }
+    }
+    return MSOC_OK;
+}
+
+static int ensure_stage(msoc_handle *h, size_t bytes)
+{
+    if (h->stage_bytes >= bytes) return MSOC_OK;
+    if (h->d_stage) cudaFree(h->d_stage);
+    h->d_stage = nullptr; h->stage_bytes = 0;
+    cudaError_t ce = cudaMalloc(&h->d_stage, bytes);
+    if (ce != cudaSuccess) return fail(MSOC_ERR_ALLOC, "state staging cudaMalloc", ce);
+    h->stage_bytes = bytes;
+    return MSOC_OK;
+}
+
+static int check_idx(const msoc_handle *h, const int64_t *idx, int64_t n, const char *who)
+{
+    if (!h || !idx || n <= 0) return fail(MSOC_ERR_INVALID, who);
+    for (int64_t i = 0; i < n; i++)
+        if (idx[i] < 0 || idx[i] >= h->n) return fail(MSOC_ERR_INVALID, "env index out of range");
+    return MSOC_OK;
+}
+
+int msoc_get_state(msoc_handle *h, const int64_t *h_idx, int64_t n, msoc_env_state *h_out)
+{
+    int rc = check_idx(h, h_idx, n, "msoc_get_state: bad argument");
+    if (rc != MSOC_OK) return rc;
+    if (!h_out) return fail(MSOC_ERR_INVALID, "msoc_get_state: null output");
+    DeviceGuard guard(h->device);
+    const size_t ib = align_up((size_t)n * sizeof(int64_t)), sb = (size_t)n * sizeof(msoc_env_state);
+    rc = ensure_stage(h, ib + sb);
+    if (rc != MSOC_OK) return rc;
+    int64_t *d_idx = (int64_t *)h->d_stage;
+    msoc_env_state *d_s = (msoc_env_state *)((char *)h->d_stage + ib);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(d_idx, h_idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    msoc_get_state_kernel<<<(unsigned)((n + 127) / 128), 128>>>(h->A, h->cur, d_idx, n, d_s);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(h_out, d_s, sb, cudaMemcpyDeviceToHost));
+    return MSOC_OK;
+}
+
+int msoc_set_state(msoc_handle *h, const int64_t *h_idx, int64_t n, const msoc_env_state *h_in)
+{
+    int rc = check_idx(h, h_idx, n, "msoc_set_state: bad argument");
+    if (rc != MSOC_OK) return rc;
+    if (!h_in) return fail(MSOC_ERR_INVALID, "msoc_set_state: null input");
+    DeviceGuard guard(h->device);
+    const size_t ib = align_up((size_t)n * sizeof(int64_t)), sb = (size_t)n * sizeof(msoc_env_state);
+    rc = ensure_stage(h, ib + sb);
+    if (rc != MSOC_OK) return rc;
+    int64_t *d_idx = (int64_t *)h->d_stage;
+    msoc_env_state *d_s = (msoc_env_state *)((char *)h->d_stage + ib);
+    /* wrap angles on the host in double (the reference keeps them unwrapped) */
+    std::vector<msoc_env_state> tmp(h_in, h_in + n);
+    for (auto &S : tmp)
+        for (int i = 0; i < 4; i++) {
+            double a = (double)S.ang[i];
+            if (a > 3.14159274101257324 || a < -3.14159274101257324) a = atan2(sin(a), cos(a));
+            S.ang[i] = (float)a;
+        }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(d_idx, h_idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_s, tmp.data(), sb, cudaMemcpyHostToDevice));
+    msoc_set_state_kernel<<<(unsigned)((n + 127) / 128), 128>>>(h->A, h->cur, d_idx, n, d_s);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    return MSOC_OK;
+}
+
+int msoc_get_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, float *h_obs)
+{
+    int rc = check_idx(h, h_idx, n, "msoc_get_obs_host: bad argument");
+    if (rc != MSOC_OK) return rc;
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int64_t i = 0; i < n; i++)
+        CUDA_TRY(cudaMemcpy(h_obs + i * 4 * OBS, h->d_obs + h_idx[i] * 4 * OBS, 4 * OBS * sizeof(float), cudaMemcpyDeviceToHost));
+    return MSOC_OK;
+}
+
+int msoc_set_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, const float *h_obs)
+{
+    int rc = check_idx(h, h_idx, n, "msoc_set_obs_host: bad argument");
+    if (rc != MSOC_OK) return rc;
+    DeviceGuard guard(h->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int64_t i = 0; i < n; i++)
+        CUDA_TRY(cudaMemcpy(h->d_obs + h_idx[i] * 4 * OBS, h_obs + i * 4 * OBS, 4 * OBS * sizeof(float), cudaMemcpyHostToDevice));
+    return MSOC_OK;
+}
+
+int msoc_device_buffers(msoc_handle *h, msoc_buffers *out)
+{
+    if (!h || !out) return fail(MSOC_ERR_INVALID, "msoc_device_buffers: null argument");
+    out->obs = h->d_obs; out->actions = h->d_act; out->reward = h->d_rew; out->done = h->d_done;
+    out->goal = h->d_goal; out->score = h->d_score; out->mask = h->d_mask; out->stats = h->d_stats;
+    return MSOC_OK;
+}
+
+int msoc_stats_device(msoc_handle *h, double *d_out, int reset, void *stream)
+{
+    if (!h || !d_out) return fail(MSOC_ERR_INVALID, "msoc_stats_device: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(d_out, h->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (reset) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(double), st));
+    return MSOC_OK;
+}
+
+int msoc_stats_read(msoc_handle *h, msoc_stats *h_out, int reset, void *stream)
+{
+    if (!h || !h_out) return fail(MSOC_ERR_INVALID, "msoc_stats_read: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h_out, h->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (reset) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(double), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MSOC_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,982 @@
+/*
+ * step_core.cuh -- per-env arithmetic of the fused soccer step (fp32), shared by every kernel in
+ * msoc.cu.  One logical env = one thread; all functions are __host__ __device__ so that the very same
+ * arithmetic can also be compiled into the TEST-ONLY host harness tests/hostsim (used to debug
+ * parity against the oracle on machines without a GPU; the product never loads it).
+ *
+ * What is restated here (reference paths relative to soccer_simulation/):
+ *   soccer_env.py:118-125      action clip + scale in float32
+ *   game/game.py:378-437       Game.step (reward state, forces, space.step, goal, reward, soft reset,
+ *                              truncation at max_steps)
+ *   game/game.py:399           pymunk Space.step(1/60): Chipmunk2D cpSpaceStep restricted to this scene
+ *                              (5 dynamic bodies, 8 static segments), see SURVEY.md Appendix A
+ *   game/entities.py:19-28,69-77  custom velocity functions (friction, max_velocity clamp)
+ *   game/game.py:129-249       the three spawn modes (Philox4x32-10 instead of PCG64)
+ *   game/game.py:258-322       22-float observation frame
+ *   marl_vecenv.py:45-53       auto-reset in full-random mode
+ *
+ * fp32 design notes (the reference computes in fp64):
+ *   - narrow phase runs in a frame centred on one of the two bodies so that no O(800) world
+ *     coordinate enters a cancellation; contact arms r1/r2 come out of it directly;
+ *   - reward shaping (difference of two nearly equal distances, game/game.py:338,345) is computed
+ *     from the step displacement:  d_prev - d_cur = -(2 D.dl + dl.dl) / (d_prev + d_cur);
+ *   - agent angles are kept wrapped to [-pi, pi] (Cody-Waite 2*pi), the reference keeps them
+ *     unwrapped and wraps only in the observation (game/game.py:271-273).
+ */
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define MSOC_HD __host__ __device__ __forceinline__
+#define MSOC_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define MSOC_HD inline
+#define MSOC_HD_NOINLINE static
+#endif
+
+namespace msoc {
+
+/* ------------------------------------------------------------------ constants (game/constants.py) */
+constexpr float SCREEN_W = 800.0f, SCREEN_H = 600.0f, FIELD_MARGIN = 10.0f;
+constexpr float GOAL_Y_BOT = 225.0f, GOAL_Y_TOP = 375.0f; /* 300 -+ 150/2 */
+constexpr float AGENT_HALF = 15.0f, BALL_R = 10.0f;
+constexpr float FIELD_L = 10.0f, FIELD_R = 790.0f, FIELD_B = 10.0f, FIELD_T = 590.0f;
+constexpr float DT = (float)(1.0 / 60.0);
+constexpr float PI_F = 3.14159274101257324f;      /* float(pi) */
+constexpr float TWO_PI_HI = 6.28318548202514648f; /* float(2 pi) */
+constexpr float TWO_PI_LO = -1.74845553e-7f;      /* 2 pi - TWO_PI_HI */
+constexpr float SLOP = 0.1f;                      /* cpSpace collisionSlop */
+constexpr float BIAS_COEF_OVER_DT = 0.1f * 60.0f; /* (1 - collisionBias^dt) / dt, collisionBias = 0.9^60 */
+constexpr int SOLVER_ITERS = 10;                  /* cpSpace iterations default */
+
+constexpr int N_AGENTS = 4, BALL = 4, STATIC_BODY = 5;
+constexpr int FRAME = 22, OBS = 66;
+constexpr int MAXC = 24;      /* contacts solved per env and step */
+constexpr int MAX_CACHE = 32; /* == MSOC_MAX_CACHE */
+
+/* pair ids (shared with the oracle and include/msoc.h) */
+constexpr int PAIR_AGENT_SEG = 0, PAIR_AGENT_AGENT = 32, PAIR_BALL_AGENT = 38, PAIR_BALL_WALL = 42;
+
+/* restitution / friction products (cpArbiterUpdate: e = ea*eb, u = ua*ub) */
+constexpr float E_AGENT_SEG = (float)(0.95 * 0.2), U_AGENT_WALL = (float)(0.2 * 0.8), U_AGENT_GOALLINE = 0.0f;
+constexpr float E_AGENT_AGENT = (float)(0.2 * 0.2), U_AGENT_AGENT = (float)(0.8 * 0.8);
+constexpr float E_BALL_AGENT = (float)(0.95 * 0.2), U_BALL_AGENT = (float)(0.2 * 0.8);
+constexpr float E_BALL_WALL = (float)(0.95 * 0.95), U_BALL_WALL = (float)(0.2 * 0.2);
+
+/* flags word of the per-env counters */
+constexpr uint32_t FLAG_CACHE_MASK = 63u, FLAG_MODE_SHIFT = 6, FLAG_MODE_MASK = 3u << 6, FLAG_HAS_BIAS = 1u << 8;
+
+/* device-side config: config.json keys as floats plus derived reciprocals */
+struct SimCfg {
+    float max_velocity, agent_minv, ball_minv, agent_iinv, ball_iinv;
+    float agent_friction, ball_friction, force_max, torque_max, max_ang_vel;
+    float prox_mult, move_mult, goal_reward, conceded_penalty, alive_penalty, score_diff_mult;
+    int32_t max_steps;
+    int32_t pad;
+};
+
+/* struct-of-arrays state of N envs (device memory in the product, host memory in tests/hostsim) */
+struct Arrays {
+    int64_t n;
+    float4 *body[5];   /* (px, py, vx, vy) of agent_0..3, ball */
+    float4 *ang;       /* agent angles, wrapped */
+    float4 *angvel;    /* agent angular velocities */
+    float2 *ballw_ret; /* (ball angular velocity, running episode return) */
+    int4 *counters;    /* (steps, score_blue, score_red, flags) */
+    float4 *vb01, *vb23, *vb4w; /* v_bias agents 0-1, 2-3; (v_bias ball, w_bias agent 0-1) */
+    float2 *wb23;      /* w_bias agents 2-3 */
+    uint64_t *seed;    /* per-env Philox key */
+    uint32_t *spawn_count;
+    uint32_t *cache_info[2]; /* [MAX_CACHE][n], ping-pong */
+    float *cache_jn[2], *cache_jt[2];
+};
+
+struct Env {
+    float px[5], py[5], vx[5], vy[5];
+    float ang[4], w[5];
+    float vbx[5], vby[5], wb[4];
+    float ep_return;
+    int32_t steps, score_b, score_r;
+    uint32_t flags;
+};
+
+/* ------------------------------------------------------------------------------------ small math */
+struct V2 { float x, y; };
+MSOC_HD V2 mk(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+MSOC_HD V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+MSOC_HD V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+MSOC_HD V2 operator*(V2 a, float s) { return mk(a.x * s, a.y * s); }
+MSOC_HD V2 vneg(V2 a) { return mk(-a.x, -a.y); }
+MSOC_HD float vdot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+MSOC_HD float vcross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+MSOC_HD V2 vperp(V2 a) { return mk(-a.y, a.x); }
+MSOC_HD V2 vrot(V2 a, V2 r) { return mk(a.x * r.x - a.y * r.y, a.x * r.y + a.y * r.x); }
+MSOC_HD V2 vlerp(V2 a, V2 b, float t) { return a * (1.0f - t) + b * t; }
+MSOC_HD float clamp01(float t) { return fminf(fmaxf(t, 0.0f), 1.0f); }
+
+MSOC_HD void sincos_f(float a, float *s, float *c)
+{
+#if defined(__CUDA_ARCH__)
+    sincosf(a, s, c);
+#else
+    *s = sinf(a); *c = cosf(a);
+#endif
+}
+MSOC_HD float rsqrt_f(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+MSOC_HD float wrap_angle(float a)
+{
+    if (a > PI_F) a = (a - TWO_PI_HI) - TWO_PI_LO;
+    else if (a < -PI_F) a = (a + TWO_PI_HI) + TWO_PI_LO;
+    return a;
+}
+
+/* --------------------------------------------------------------------------------------- Philox */
+MSOC_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+MSOC_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+MSOC_HD float uni(uint32_t x, float lo, float hi) { return fmaf(u01(x), hi - lo, lo); }
+
+/* Spawn positions for one of the three modes (game/game.py:129-249).  Draw order and
+   distributions follow the reference; the stream is Philox keyed by (seed, global env index,
+   spawn counter).  Returns the incremented spawn counter. */
+MSOC_HD_NOINLINE uint32_t spawn_positions(int mode, uint64_t seed, uint64_t gidx, uint32_t spawn_count, float *px, float *py)
+{
+    if (mode == 1) { /* fixed, game/game.py:129-152 */
+        px[0] = 200.0f; py[0] = 198.0f; px[1] = 200.0f; py[1] = 396.0f;
+        px[2] = 600.0f; py[2] = 198.0f; px[3] = 600.0f; py[3] = 396.0f;
+        px[4] = 400.0f; py[4] = 300.0f;
+        return spawn_count;
+    }
+    uint32_t A[4], B[4], C[4], D[4];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t g0 = (uint32_t)gidx, g1 = (uint32_t)(gidx >> 32);
+    philox4x32_10(g0, g1, spawn_count, 0, k0, k1, A);
+    philox4x32_10(g0, g1, spawn_count, 1, k0, k1, B);
+    philox4x32_10(g0, g1, spawn_count, 2, k0, k1, C);
+    philox4x32_10(g0, g1, spawn_count, 3, k0, k1, D);
+    const float xmin = 30.0f, xmax = 770.0f, ymin = 30.0f, ymax = 570.0f;
+    if (mode == 2) { /* full random, game/game.py:192-249 */
+        const bool corners = u01(A[0]) < 0.75f;
+        for (int k = 0; k < 2; k++) {
+            if (corners) {
+                const uint32_t c = A[1 + k] >> 30;
+                const bool left = (c == 0 || c == 1), top = (c == 0 || c == 2);
+                const float cx = left ? 18.0f : 782.0f, cy = top ? 582.0f : 18.0f;
+                px[k] = cx + uni(B[2 * k], -5.0f, 5.0f);
+                py[k] = cy + uni(B[2 * k + 1], -5.0f, 5.0f);
+            } else {
+                px[k] = uni(B[2 * k], xmin, xmax);
+                py[k] = uni(B[2 * k + 1], ymin, ymax);
+            }
+        }
+        for (int k = 0; k < 2; k++) { px[2 + k] = uni(C[2 * k], xmin, xmax); py[2 + k] = uni(C[2 * k + 1], ymin, ymax); }
+        px[4] = uni(D[0], xmin, xmax); py[4] = uni(D[1], ymin, ymax);
+    } else { /* default half-field random, game/game.py:154-190 */
+        for (int k = 0; k < 2; k++) { px[k] = uni(B[2 * k], 30.0f, 380.0f); py[k] = uni(B[2 * k + 1], ymin, ymax); }
+        for (int k = 0; k < 2; k++) { px[2 + k] = uni(C[2 * k], 420.0f, 770.0f); py[2 + k] = uni(C[2 * k + 1], ymin, ymax); }
+        px[4] = 400.0f + uni(D[0], -40.0f, 40.0f); py[4] = 300.0f + uni(D[1], -40.0f, 40.0f);
+    }
+    return spawn_count + 1;
+}
+
+/* -------------------------------------------------------------------------------- state load/store */
+MSOC_HD void load_env(const Arrays &A, int64_t e, Env &E)
+{
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const float4 b = A.body[i][e];
+        E.px[i] = b.x; E.py[i] = b.y; E.vx[i] = b.z; E.vy[i] = b.w;
+    }
+    const float4 a = A.ang[e], w = A.angvel[e];
+    E.ang[0] = a.x; E.ang[1] = a.y; E.ang[2] = a.z; E.ang[3] = a.w;
+    E.w[0] = w.x; E.w[1] = w.y; E.w[2] = w.z; E.w[3] = w.w;
+    const float2 br = A.ballw_ret[e];
+    E.w[4] = br.x; E.ep_return = br.y;
+    const int4 c = A.counters[e];
+    E.steps = c.x; E.score_b = c.y; E.score_r = c.z; E.flags = (uint32_t)c.w;
+    if (E.flags & FLAG_HAS_BIAS) {
+        const float4 b01 = A.vb01[e], b23 = A.vb23[e], b4w = A.vb4w[e];
+        const float2 w23 = A.wb23[e];
+        E.vbx[0] = b01.x; E.vby[0] = b01.y; E.vbx[1] = b01.z; E.vby[1] = b01.w;
+        E.vbx[2] = b23.x; E.vby[2] = b23.y; E.vbx[3] = b23.z; E.vby[3] = b23.w;
+        E.vbx[4] = b4w.x; E.vby[4] = b4w.y; E.wb[0] = b4w.z; E.wb[1] = b4w.w;
+        E.wb[2] = w23.x; E.wb[3] = w23.y;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 5; i++) { E.vbx[i] = 0.0f; E.vby[i] = 0.0f; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) E.wb[i] = 0.0f;
+    }
+}
+
+MSOC_HD void store_env(const Arrays &A, int64_t e, Env &E)
+{
+    bool any_bias = false;
+#pragma unroll
+    for (int i = 0; i < 5; i++) any_bias = any_bias || (E.vbx[i] != 0.0f) || (E.vby[i] != 0.0f);
+#pragma unroll
+    for (int i = 0; i < 4; i++) any_bias = any_bias || (E.wb[i] != 0.0f);
+    if (any_bias) {
+        A.vb01[e] = make_float4(E.vbx[0], E.vby[0], E.vbx[1], E.vby[1]);
+        A.vb23[e] = make_float4(E.vbx[2], E.vby[2], E.vbx[3], E.vby[3]);
+        A.vb4w[e] = make_float4(E.vbx[4], E.vby[4], E.wb[0], E.wb[1]);
+        A.wb23[e] = make_float2(E.wb[2], E.wb[3]);
+        E.flags |= FLAG_HAS_BIAS;
+    } else {
+        E.flags &= ~FLAG_HAS_BIAS;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) A.body[i][e] = make_float4(E.px[i], E.py[i], E.vx[i], E.vy[i]);
+    A.ang[e] = make_float4(E.ang[0], E.ang[1], E.ang[2], E.ang[3]);
+    A.angvel[e] = make_float4(E.w[0], E.w[1], E.w[2], E.w[3]);
+    A.ballw_ret[e] = make_float2(E.w[4], E.ep_return);
+    A.counters[e] = make_int4(E.steps, E.score_b, E.score_r, (int)E.flags);
+}
+
+/* ----------------------------------------------------------------------------- observation frame */
+/* game/game.py:258-322; frames for all four agents, 22 floats each.  Pairwise agent vectors are
+   computed once and mirrored.  STRIDE is the distance between two agents' frames in `out`. */
+MSOC_HD void unit_mag(float dx, float dy, float &ux, float &uy, float &mag)
+{
+    const float d2 = dx * dx + dy * dy;
+    if (d2 > 1e-16f) { /* mag > 1e-8, game/game.py:281 */
+        const float inv = rsqrt_f(d2);
+        ux = dx * inv; uy = dy * inv; mag = d2 * inv * 0.001f; /* / hypot(800, 600) */
+    } else { ux = 0.0f; uy = 0.0f; mag = 0.0f; }
+}
+
+template <int STRIDE>
+MSOC_HD void make_frames(const Env &E, const SimCfg &c, float *out)
+{
+    const float vmax = fmaxf(c.max_velocity, 1e-6f), wmax = fmaxf(c.max_ang_vel, 1e-6f);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float *o = out + i * STRIDE;
+        o[0] = E.vx[i] / vmax;
+        o[1] = E.vy[i] / vmax;
+        o[2] = E.ang[i] / PI_F;
+        o[3] = E.w[i] / wmax;
+    }
+    /* agent-agent vectors: slot of j in i's frame */
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = i + 1; j < 4; j++) {
+            float ux, uy, m;
+            unit_mag(E.px[j] - E.px[i], E.py[j] - E.py[i], ux, uy, m);
+            /* teammate: 0<->1, 2<->3 (slot 4); opponents in index order (slots 7, 10) */
+            const bool mates = (i == 0 && j == 1) || (i == 2 && j == 3);
+            const int slot_i = mates ? 4 : (7 + 3 * (j & 1)); /* i sees opponent j: j=2/0 -> 7, j=3/1 -> 10 */
+            const int slot_j = mates ? 4 : (7 + 3 * (i & 1));
+            float *oi = out + i * STRIDE + slot_i, *oj = out + j * STRIDE + slot_j;
+            oi[0] = ux; oi[1] = uy; oi[2] = m;
+            oj[0] = -ux; oj[1] = -uy; oj[2] = m;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float *o = out + i * STRIDE;
+        unit_mag(E.px[4] - E.px[i], E.py[4] - E.py[i], o[13], o[14], o[15]);
+        const float own_x = (i < 2) ? FIELD_L : FIELD_R, opp_x = (i < 2) ? FIELD_R : FIELD_L;
+        unit_mag(own_x - E.px[i], 300.0f - E.py[i], o[16], o[17], o[18]);
+        unit_mag(opp_x - E.px[i], 300.0f - E.py[i], o[19], o[20], o[21]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ narrow phase */
+struct Manifold { int count; V2 n; V2 p1[2], p2[2]; int key[2]; };
+struct Edge { V2 pa, pb; int ia, ib; float r; };
+/* box in some frame: v[k] vertices in cpBoxShapeInit2 order, nrm[k] = outward normal of edge k-1 -> k */
+struct Box { V2 v[4]; V2 nrm[4]; };
+
+MSOC_HD void make_box(float cs, float sn, V2 off, Box &b)
+{
+    const float h = AGENT_HALF;
+    const V2 a = mk(h * cs + h * sn, h * sn - h * cs); /* R (h,-h) */
+    const V2 d = mk(h * cs - h * sn, h * sn + h * cs); /* R (h, h) */
+    b.v[0] = off + a; b.v[1] = off + d; b.v[2] = off - a; b.v[3] = off - d;
+    b.nrm[0] = mk(sn, -cs); b.nrm[1] = mk(cs, sn); b.nrm[2] = mk(-sn, cs); b.nrm[3] = mk(-cs, -sn);
+}
+
+/* Closest features of two convex polygons (a segment is a 2-gon): the (n, d) Chipmunk's GJK
+   (separated) / EPA (overlapping) converge to.  nA[k] / nB[k] are unit outward normals of the edge
+   k -> k+1, il2 = 1/|edge|^2 (all edges of one shape have the same length here). */
+template <int NA, int NB>
+MSOC_HD void closest_convex(const V2 *A, const V2 *nA, float il2A, const V2 *B, const V2 *nB, float il2B, V2 &n_out, float &d_out)
+{
+    float best = -INFINITY; V2 bn = mk(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+        float s = INFINITY;
+#pragma unroll
+        for (int j = 0; j < NB; j++) s = fminf(s, vdot(B[j] - A[k], nA[k]));
+        if (s > best) { best = s; bn = nA[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        float s = INFINITY;
+#pragma unroll
+        for (int i = 0; i < NA; i++) s = fminf(s, vdot(A[i] - B[k], nB[k]));
+        if (s > best) { best = s; bn = vneg(nB[k]); }
+    }
+    if (best <= 0.0f) { n_out = bn; d_out = best; return; }
+    float bd2 = INFINITY; V2 bdel = bn;
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+        const V2 e = A[(k + 1) % NA] - A[k];
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const V2 rel = B[j] - A[k];
+            const float tr = vdot(rel, e) * il2A, t = clamp01(tr);
+            /* interior foot point: the offset is exactly along the edge normal (no cancellation of the
+               O(800) along-edge component, which would tilt n when the vertex nearly touches the edge) */
+            const V2 delta = (tr == t) ? nA[k] * vdot(rel, nA[k]) : rel - e * t;
+            const float d2 = vdot(delta, delta);
+            if (d2 < bd2) { bd2 = d2; bdel = delta; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const V2 e = B[(k + 1) % NB] - B[k];
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            const V2 rel = A[i] - B[k];
+            const float tr = vdot(rel, e) * il2B, t = clamp01(tr);
+            const V2 delta = (tr == t) ? nB[k] * (-vdot(rel, nB[k])) : e * t - rel;
+            const float d2 = vdot(delta, delta);
+            if (d2 < bd2) { bd2 = d2; bdel = delta; }
+        }
+    }
+    const float inv = rsqrt_f(bd2);
+    n_out = bdel * inv; d_out = bd2 * inv;
+}
+
+MSOC_HD Edge support_edge_poly(const Box &b, V2 n)
+{
+    /* cpCollision.c SupportEdgeForPoly */
+    float mx = -INFINITY; int i1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float d = vdot(b.v[i], n); if (d > mx) { mx = d; i1 = i; } }
+    const int i0 = (i1 + 3) & 3, i2 = (i1 + 1) & 3;
+    /* dynamic selects instead of dynamic indexing */
+    V2 v0, v1, v2, n1, n2;
+    v1 = (i1 == 0) ? b.v[0] : (i1 == 1) ? b.v[1] : (i1 == 2) ? b.v[2] : b.v[3];
+    v0 = (i0 == 0) ? b.v[0] : (i0 == 1) ? b.v[1] : (i0 == 2) ? b.v[2] : b.v[3];
+    v2 = (i2 == 0) ? b.v[0] : (i2 == 1) ? b.v[1] : (i2 == 2) ? b.v[2] : b.v[3];
+    n1 = (i1 == 0) ? b.nrm[0] : (i1 == 1) ? b.nrm[1] : (i1 == 2) ? b.nrm[2] : b.nrm[3];
+    n2 = (i2 == 0) ? b.nrm[0] : (i2 == 1) ? b.nrm[1] : (i2 == 2) ? b.nrm[2] : b.nrm[3];
+    Edge e; e.r = 0.0f;
+    if (vdot(n, n1) > vdot(n, n2)) { e.pa = v0; e.ia = i0; e.pb = v1; e.ib = i1; }
+    else                           { e.pa = v1; e.ia = i1; e.pb = v2; e.ib = i2; }
+    return e;
+}
+
+MSOC_HD void contact_points(const Edge &e1, const Edge &e2, V2 n, float d, Manifold &m)
+{
+    /* cpCollision.c ContactPoints; key = (vertex on shape a) * 4 + (vertex on shape b) */
+    m.count = 0;
+    const float mindist = e1.r + e2.r;
+    if (!(d <= mindist)) return;
+    m.n = n;
+    const float d_e1_a = vcross(e1.pa, n), d_e1_b = vcross(e1.pb, n);
+    const float d_e2_a = vcross(e2.pa, n), d_e2_b = vcross(e2.pb, n);
+    const float e1_denom = 1.0f / (d_e1_b - d_e1_a + FLT_MIN);
+    const float e2_denom = 1.0f / (d_e2_b - d_e2_a + FLT_MIN);
+    {
+        const V2 p1 = n * e1.r + vlerp(e1.pa, e1.pb, clamp01((d_e2_b - d_e1_a) * e1_denom));
+        const V2 p2 = n * (-e2.r) + vlerp(e2.pa, e2.pb, clamp01((d_e1_a - d_e2_a) * e2_denom));
+        if (vdot(p2 - p1, n) <= 0.0f) { m.p1[0] = p1; m.p2[0] = p2; m.key[0] = e1.ia * 4 + e2.ib; m.count = 1; }
+    }
+    {
+        const V2 p1 = n * e1.r + vlerp(e1.pa, e1.pb, clamp01((d_e2_a - d_e1_a) * e1_denom));
+        const V2 p2 = n * (-e2.r) + vlerp(e2.pa, e2.pb, clamp01((d_e1_b - d_e2_a) * e2_denom));
+        if (vdot(p2 - p1, n) <= 0.0f) {
+            const int k = e1.ib * 4 + e2.ia;
+            if (m.count == 0) { m.p1[0] = p1; m.p2[0] = p2; m.key[0] = k; }
+            else              { m.p1[1] = p1; m.p2[1] = p2; m.key[1] = k; }
+            m.count++;
+        }
+    }
+}
+
+/* static segments in setup_field order (game/game.py:50-68) */
+struct Seg { V2 a, b, n; float r, il2, u; };
+MSOC_HD Seg get_segment(int s)
+{
+    Seg g;
+    if (s < 2) {
+        const float y = (s == 0) ? FIELD_B : FIELD_T;
+        g.a = mk(FIELD_L, y); g.b = mk(FIELD_R, y); g.n = mk(0.0f, -1.0f);
+        g.il2 = 1.0f / (780.0f * 780.0f);
+    } else {
+        const float x = (s == 2 || s == 3 || s == 6) ? FIELD_L : FIELD_R;
+        const float y0 = (s == 2 || s == 4) ? FIELD_B : (s == 3 || s == 5) ? GOAL_Y_TOP : GOAL_Y_BOT;
+        const float y1 = (s == 2 || s == 4) ? GOAL_Y_BOT : (s == 3 || s == 5) ? FIELD_T : GOAL_Y_TOP;
+        g.a = mk(x, y0); g.b = mk(x, y1); g.n = mk(1.0f, 0.0f);
+        const float len = y1 - y0;
+        g.il2 = 1.0f / (len * len);
+    }
+    g.r = (s < 6) ? 2.0f : 1.0f;
+    g.u = (s < 6) ? U_AGENT_WALL : U_AGENT_GOALLINE;
+    return g;
+}
+
+/* cpCollision.c SegmentToPoly (a = segment, b = box), in the frame centred on the box.
+   p1 is on the segment side, p2 on the box side; both relative to the box centre. */
+MSOC_HD void collide_segment_box(const Seg &g, V2 c, float cs, float sn, Manifold &m)
+{
+    Box box; make_box(cs, sn, mk(0.0f, 0.0f), box);
+    const V2 sv[2] = {g.a - c, g.b - c};
+    const V2 sn2[2] = {g.n, vneg(g.n)};
+    const V2 bn[4] = {box.nrm[1], box.nrm[2], box.nrm[3], box.nrm[0]};
+    V2 n; float d;
+    closest_convex<2, 4>(sv, sn2, g.il2, box.v, bn, 1.0f / 900.0f, n, d);
+    m.count = 0;
+    if (d - g.r <= 0.0f) {
+        Edge e1; e1.r = g.r;
+        if (vdot(g.n, n) > 0.0f) { e1.pa = sv[0]; e1.ia = 0; e1.pb = sv[1]; e1.ib = 1; }
+        else                     { e1.pa = sv[1]; e1.ia = 1; e1.pb = sv[0]; e1.ib = 0; }
+        contact_points(e1, support_edge_poly(box, vneg(n)), n, d, m);
+    }
+}
+
+/* cpCollision.c PolyToPoly, in the frame centred on box a; off = centre_b - centre_a */
+MSOC_HD void collide_box_box(float csa, float sna, float csb, float snb, V2 off, Manifold &m)
+{
+    Box A, B; make_box(csa, sna, mk(0.0f, 0.0f), A); make_box(csb, snb, off, B);
+    const V2 an[4] = {A.nrm[1], A.nrm[2], A.nrm[3], A.nrm[0]};
+    const V2 bn[4] = {B.nrm[1], B.nrm[2], B.nrm[3], B.nrm[0]};
+    V2 n; float d;
+    closest_convex<4, 4>(A.v, an, 1.0f / 900.0f, B.v, bn, 1.0f / 900.0f, n, d);
+    m.count = 0;
+    if (d <= 0.0f) contact_points(support_edge_poly(A, n), support_edge_poly(B, vneg(n)), n, d, m);
+}
+
+/* cpCollision.c CircleToPoly (a = ball, b = box), frame centred on the box; c = ball centre.
+   p1 = point on the ball, p2 = point on the box. */
+MSOC_HD void collide_ball_box(V2 c, float cs, float sn, Manifold &m)
+{
+    Box box; make_box(cs, sn, mk(0.0f, 0.0f), box);
+    m.count = 0;
+    float best = -INFINITY; int bk = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float s = vdot(c - box.v[k], box.nrm[k]); if (s > best) { best = s; bk = k; } }
+    V2 n, pb; float d;
+    if (best <= 0.0f) { /* centre inside the box */
+        const V2 nk = (bk == 0) ? box.nrm[0] : (bk == 1) ? box.nrm[1] : (bk == 2) ? box.nrm[2] : box.nrm[3];
+        n = vneg(nk); d = best; pb = c - nk * best;
+    } else {
+        float bd2 = INFINITY; pb = c;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const V2 a0 = box.v[(k + 3) & 3], e = box.v[k] - a0;
+            const V2 rel = c - a0;
+            const float tr = vdot(rel, e) * (1.0f / 900.0f), t = clamp01(tr);
+            const V2 q = (tr == t) ? c - box.nrm[k] * vdot(rel, box.nrm[k]) : a0 + e * t;
+            const V2 dl = q - c;
+            const float d2 = vdot(dl, dl);
+            if (d2 < bd2) { bd2 = d2; pb = q; }
+        }
+        const float inv = rsqrt_f(bd2);
+        d = bd2 * inv; n = (pb - c) * inv;
+    }
+    if (d <= BALL_R) { m.count = 1; m.n = n; m.key[0] = 0; m.p1[0] = c + n * BALL_R; m.p2[0] = pb; }
+}
+
+/* cpCollision.c CircleToSegment (a = ball, b = wall), frame centred on the ball. */
+MSOC_HD void collide_ball_segment(const Seg &g, V2 c, Manifold &m)
+{
+    const V2 a = g.a - c, sd = g.b - g.a;
+    const float tr = -vdot(sd, a) * g.il2, t = clamp01(tr);
+    /* closest point relative to the ball centre; interior foot point exactly along the wall normal */
+    const V2 closest = (tr == t) ? g.n * vdot(a, g.n) : a + sd * t;
+    const float mind = BALL_R + g.r;
+    const float d2 = vdot(closest, closest);
+    m.count = 0;
+    if (d2 < mind * mind) {
+        V2 n = g.n;
+        if (d2 > 0.0f) n = closest * rsqrt_f(d2);
+        m.count = 1; m.n = n; m.key[0] = 0;
+        m.p1[0] = n * BALL_R;
+        m.p2[0] = closest - n * g.r;
+    }
+}
+
+/* ---------------------------------------------------------------------------------- solver storage */
+/* Per-thread scratch with dynamic indexing (local memory in v1). */
+struct Work {
+    /* solver bodies; index 5 = the static body (inverse mass 0) */
+    float bvx[6], bvy[6], bw[6], bbx[6], bby[6], bbw[6], bmi[6], bii[6];
+    /* contacts */
+    float r1x[MAXC], r1y[MAXC], r2x[MAXC], r2y[MAXC], nx[MAXC], ny[MAXC];
+    float nMass[MAXC], tMass[MAXC], bounce[MAXC], bias[MAXC], jn[MAXC], jt[MAXC], jb[MAXC], u[MAXC];
+    uint32_t meta[MAXC]; /* a | b<<3 | pair<<6 | key<<12 | first<<16 */
+    int nc, overflow;
+    uint64_t touched;
+};
+
+struct CacheIO {
+    const uint32_t *old_info; const float *old_jn, *old_jt; /* [MAX_CACHE][n] */
+    uint32_t *new_info; float *new_jn, *new_jt;
+    int64_t n, e;
+    int old_count;
+};
+
+/* cpSpaceCollideShapes + cpArbiterUpdate for one touching pair: append the manifold's contacts,
+   carry jnAcc/jtAcc of equal-key contacts from the cache, decide first-contact state. */
+MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, float u, const Manifold &m,
+                          V2 r1_off, V2 r2_off)
+{
+    W.touched |= (1ull << pair);
+    bool first = true;
+    float cjn[2] = {0.0f, 0.0f}, cjt[2] = {0.0f, 0.0f};
+    for (int j = 0; j < cio.old_count; j++) {
+        const uint32_t info = cio.old_info[(int64_t)j * cio.n + cio.e];
+        if ((int)(info & 63u) != pair) continue;
+        if (((info >> 10) & 3u) == 0u) first = false;
+        const int key = (int)((info >> 6) & 15u);
+        const float ojn = cio.old_jn[(int64_t)j * cio.n + cio.e], ojt = cio.old_jt[(int64_t)j * cio.n + cio.e];
+        if (m.count > 0 && key == m.key[0]) { cjn[0] = ojn; cjt[0] = ojt; }
+        if (m.count > 1 && key == m.key[1]) { cjn[1] = ojn; cjt[1] = ojt; }
+    }
+    for (int i = 0; i < m.count; i++) {
+        if (W.nc >= MAXC) { W.overflow++; continue; }
+        const int k = W.nc++;
+        const V2 p1 = (i == 0) ? m.p1[0] : m.p1[1], p2 = (i == 0) ? m.p2[0] : m.p2[1];
+        const int key = (i == 0) ? m.key[0] : m.key[1];
+        W.r1x[k] = p1.x - r1_off.x; W.r1y[k] = p1.y - r1_off.y;
+        W.r2x[k] = p2.x - r2_off.x; W.r2y[k] = p2.y - r2_off.y;
+        W.nx[k] = m.n.x; W.ny[k] = m.n.y;
+        W.jn[k] = (i == 0) ? cjn[0] : cjn[1];
+        W.jt[k] = (i == 0) ? cjt[0] : cjt[1];
+        W.jb[k] = 0.0f;
+        W.u[k] = u;
+        W.bounce[k] = e; /* restitution until the pre-step turns it into the bounce velocity */
+        /* signed separation along n from the contact points themselves (translation invariant):
+           cpArbiterPreStep dist = ((r2 - r1) + (pb - pa)) . n */
+        W.bias[k] = vdot(p2 - p1, m.n);
+        W.meta[k] = (uint32_t)a | ((uint32_t)b << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16);
+    }
+}
+
+MSOC_HD bool bb_overlap(float cx, float cy, float R, float l, float b, float r, float t)
+{
+    return (cx - R <= r) && (l <= cx + R) && (cy - R <= t) && (b <= cy + R);
+}
+
+/* ------------------------------------------------------------------------------------------ step */
+struct StepOut {
+    float reward;
+    uint8_t done;
+    int8_t goal;
+    bool fresh_episode;   /* auto-reset happened: obs = 3 copies of the new frame */
+    float finished_return; /* blue return of the episode that ended on this step */
+    int n_contacts, overflow;
+    int32_t score_b, score_r; /* info["score"] of this step (before any auto-reset) */
+};
+
+/* Full reset of one env (Game.reset, game/game.py:76-118): bodies re-created (all velocities,
+   biases and cached arbiters dropped), spawn, counters cleared. */
+MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint32_t &spawn_count)
+{
+    float px[5], py[5];
+    spawn_count = spawn_positions(mode, seed, gidx, spawn_count, px, py);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        E.px[i] = px[i]; E.py[i] = py[i]; E.vx[i] = 0.0f; E.vy[i] = 0.0f; E.w[i] = 0.0f;
+        E.vbx[i] = 0.0f; E.vby[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { E.wb[i] = 0.0f; E.ang[i] = (i < 2) ? 0.0f : PI_F; }
+    E.steps = 0; E.score_b = 0; E.score_r = 0; E.ep_return = 0.0f;
+    E.flags = ((uint32_t)mode << FLAG_MODE_SHIFT); /* cache count 0, no bias */
+}
+
+template <int FSTRIDE>
+MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e, uint64_t gidx,
+                      uint32_t step_flags, float *frames, StepOut &out)
+{
+    /* ---- soccer_env.py:118-125: clip to [-1, 1], scale in float32 */
+    float Fx[4], Fy[4], Tq[4];
+    float cs[4], sn[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float a0 = fminf(fmaxf(act[3 * i + 0], -1.0f), 1.0f) * c.force_max;
+        const float a1 = fminf(fmaxf(act[3 * i + 1], -1.0f), 1.0f) * c.force_max;
+        Tq[i] = fminf(fmaxf(act[3 * i + 2], -1.0f), 1.0f) * c.torque_max;
+        /* apply_force_at_local_point(force, (0,0)): world force = R(angle) force, game/game.py:396 */
+        float s_, c_;
+        sincos_f(E.ang[i], &s_, &c_);
+        Fx[i] = a0 * c_ - a1 * s_;
+        Fy[i] = a0 * s_ + a1 * c_;
+    }
+    /* ---- game/game.py:379 _update_reward_state: distances at the start of the step */
+    const float d0x = E.px[0] - E.px[4], d0y = E.py[0] - E.py[4];
+    const float d1x = E.px[1] - E.px[4], d1y = E.py[1] - E.py[4];
+    const float dgx = E.px[4] - FIELD_R, dgy = E.py[4] - 300.0f;
+    E.steps += 1;
+
+    /* ---- cpBodyUpdatePosition: p += (v + v_bias) dt, a += (w + w_bias) dt, bias cleared */
+    float incx[5], incy[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        incx[i] = (E.vx[i] + E.vbx[i]) * DT; incy[i] = (E.vy[i] + E.vby[i]) * DT;
+        E.px[i] += incx[i]; E.py[i] += incy[i];
+        E.vbx[i] = 0.0f; E.vby[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        E.ang[i] = wrap_angle(E.ang[i] + (E.w[i] + E.wb[i]) * DT);
+        E.wb[i] = 0.0f;
+        sincos_f(E.ang[i], &sn[i], &cs[i]);
+    }
+
+    /* ---- broad phase (conservative bounding-box reject, cpSpaceCollideShapes QueryReject) */
+    uint32_t m_as = 0, m_aa = 0, m_ba = 0, m_bw = 0;
+    float R[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        R[i] = AGENT_HALF * (fabsf(cs[i]) + fabsf(sn[i]));
+        const float x = E.px[i], y = E.py[i], r = R[i];
+        if (x - r <= 12.0f || x + r >= 788.0f || y - r <= 12.0f || y + r >= 588.0f) {
+            uint32_t mm = 0;
+            mm |= bb_overlap(x, y, r, 8.0f, 8.0f, 792.0f, 12.0f) ? 1u : 0u;
+            mm |= bb_overlap(x, y, r, 8.0f, 588.0f, 792.0f, 592.0f) ? 2u : 0u;
+            mm |= bb_overlap(x, y, r, 8.0f, 8.0f, 12.0f, 227.0f) ? 4u : 0u;
+            mm |= bb_overlap(x, y, r, 8.0f, 373.0f, 12.0f, 592.0f) ? 8u : 0u;
+            mm |= bb_overlap(x, y, r, 788.0f, 8.0f, 792.0f, 227.0f) ? 16u : 0u;
+            mm |= bb_overlap(x, y, r, 788.0f, 373.0f, 792.0f, 592.0f) ? 32u : 0u;
+            mm |= bb_overlap(x, y, r, 9.0f, 224.0f, 11.0f, 376.0f) ? 64u : 0u;
+            mm |= bb_overlap(x, y, r, 789.0f, 224.0f, 791.0f, 376.0f) ? 128u : 0u;
+            m_as |= mm << (8 * i);
+        }
+    }
+    {
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int j = i + 1; j < 4; j++) {
+                const float rr = R[i] + R[j];
+                if (fabsf(E.px[i] - E.px[j]) <= rr && fabsf(E.py[i] - E.py[j]) <= rr) m_aa |= 1u << p;
+                p++;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float rr = R[i] + BALL_R;
+        if (fabsf(E.px[i] - E.px[4]) <= rr && fabsf(E.py[i] - E.py[4]) <= rr) m_ba |= 1u << i;
+    }
+    {
+        const float x = E.px[4], y = E.py[4], r = BALL_R;
+        if (x - r <= 12.0f || x + r >= 788.0f || y - r <= 12.0f || y + r >= 588.0f) {
+            m_bw |= bb_overlap(x, y, r, 8.0f, 8.0f, 792.0f, 12.0f) ? 1u : 0u;
+            m_bw |= bb_overlap(x, y, r, 8.0f, 588.0f, 792.0f, 592.0f) ? 2u : 0u;
+            m_bw |= bb_overlap(x, y, r, 8.0f, 8.0f, 12.0f, 227.0f) ? 4u : 0u;
+            m_bw |= bb_overlap(x, y, r, 8.0f, 373.0f, 12.0f, 592.0f) ? 8u : 0u;
+            m_bw |= bb_overlap(x, y, r, 788.0f, 8.0f, 792.0f, 227.0f) ? 16u : 0u;
+            m_bw |= bb_overlap(x, y, r, 788.0f, 373.0f, 792.0f, 592.0f) ? 32u : 0u;
+        }
+    }
+
+    const int old_count = (int)(E.flags & FLAG_CACHE_MASK);
+    int n_contacts = 0, overflow = 0;
+    int new_count = 0;
+
+    Work W;
+    W.nc = 0; W.overflow = 0; W.touched = 0ull;
+    const bool contact_path = (m_as | m_aa | m_ba | m_bw) != 0u || old_count != 0;
+    if (contact_path) {
+        CacheIO cio;
+        cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
+        cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
+        cio.n = A.n; cio.e = e; cio.old_count = old_count;
+
+        /* geometry with dynamic body index */
+        float gx[5], gy[5], gcs[4], gsn[4];
+#pragma unroll
+        for (int i = 0; i < 5; i++) { gx[i] = E.px[i]; gy[i] = E.py[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { gcs[i] = cs[i]; gsn[i] = sn[i]; }
+
+        /* narrow phase in canonical arbiter order: agent x segment (agent-major), agent x agent,
+           ball x agent, ball x wall.  Each lane walks its own candidate list. */
+        Manifold m;
+        while (m_as) {
+#if defined(__CUDA_ARCH__)
+            const int bit = __ffs((int)m_as) - 1;
+#else
+            const int bit = __builtin_ctz(m_as);
+#endif
+            m_as &= m_as - 1;
+            const int i = bit >> 3, s = bit & 7;
+            const Seg g = get_segment(s);
+            const V2 ctr = mk(gx[i], gy[i]);
+            collide_segment_box(g, ctr, gcs[i], gsn[i], m);
+            if (m.count) add_contacts(W, cio, PAIR_AGENT_SEG + bit, STATIC_BODY, i, E_AGENT_SEG, g.u, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
+        }
+        while (m_aa) {
+#if defined(__CUDA_ARCH__)
+            const int p = __ffs((int)m_aa) - 1;
+#else
+            const int p = __builtin_ctz(m_aa);
+#endif
+            m_aa &= m_aa - 1;
+            const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
+            const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
+            const V2 off = mk(gx[j] - gx[i], gy[j] - gy[i]);
+            collide_box_box(gcs[i], gsn[i], gcs[j], gsn[j], off, m);
+            if (m.count) add_contacts(W, cio, PAIR_AGENT_AGENT + p, i, j, E_AGENT_AGENT, U_AGENT_AGENT, m, mk(0.0f, 0.0f), off);
+        }
+        while (m_ba) {
+#if defined(__CUDA_ARCH__)
+            const int i = __ffs((int)m_ba) - 1;
+#else
+            const int i = __builtin_ctz(m_ba);
+#endif
+            m_ba &= m_ba - 1;
+            const V2 cb = mk(gx[4] - gx[i], gy[4] - gy[i]);
+            collide_ball_box(cb, gcs[i], gsn[i], m);
+            if (m.count) add_contacts(W, cio, PAIR_BALL_AGENT + i, BALL, i, E_BALL_AGENT, U_BALL_AGENT, m, cb, mk(0.0f, 0.0f));
+        }
+        while (m_bw) {
+#if defined(__CUDA_ARCH__)
+            const int s = __ffs((int)m_bw) - 1;
+#else
+            const int s = __builtin_ctz(m_bw);
+#endif
+            m_bw &= m_bw - 1;
+            const Seg g = get_segment(s);
+            collide_ball_segment(g, mk(gx[4], gy[4]), m);
+            if (m.count) add_contacts(W, cio, PAIR_BALL_WALL + s, BALL, STATIC_BODY, E_BALL_WALL, U_BALL_WALL, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
+        }
+        n_contacts = W.nc; overflow = W.overflow;
+
+        if (W.nc > 0) {
+            /* ---- cpArbiterPreStep with the velocities BEFORE the velocity update */
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                W.bvx[i] = E.vx[i]; W.bvy[i] = E.vy[i]; W.bw[i] = E.w[i];
+                W.bbx[i] = 0.0f; W.bby[i] = 0.0f; W.bbw[i] = 0.0f;
+                W.bmi[i] = (i < 4) ? c.agent_minv : c.ball_minv;
+                W.bii[i] = (i < 4) ? c.agent_iinv : c.ball_iinv;
+            }
+            W.bvx[5] = W.bvy[5] = W.bw[5] = W.bbx[5] = W.bby[5] = W.bbw[5] = W.bmi[5] = W.bii[5] = 0.0f;
+            for (int k = 0; k < W.nc; k++) {
+                const int a = W.meta[k] & 7u, b = (W.meta[k] >> 3) & 7u;
+                const V2 n = mk(W.nx[k], W.ny[k]), t = vperp(n);
+                const V2 r1 = mk(W.r1x[k], W.r1y[k]), r2 = mk(W.r2x[k], W.r2y[k]);
+                const float ma = W.bmi[a], ia = W.bii[a], mb = W.bmi[b], ib = W.bii[b];
+                const float r1n = vcross(r1, n), r2n = vcross(r2, n), r1t = vcross(r1, t), r2t = vcross(r2, t);
+                W.nMass[k] = 1.0f / (ma + ia * r1n * r1n + mb + ib * r2n * r2n);
+                W.tMass[k] = 1.0f / (ma + ia * r1t * r1t + mb + ib * r2t * r2t);
+                const float dist = W.bias[k];
+                W.bias[k] = -BIAS_COEF_OVER_DT * fminf(0.0f, dist + SLOP);
+                const V2 va = mk(W.bvx[a], W.bvy[a]) + vperp(r1) * W.bw[a];
+                const V2 vb = mk(W.bvx[b], W.bvy[b]) + vperp(r2) * W.bw[b];
+                W.bounce[k] = vdot(vb - va, n) * W.bounce[k];
+            }
+        }
+
+    }
+
+    /* ---- cpBodyUpdateVelocity (gravity 0, damping 1) + the reference's custom velocity functions
+       (game/entities.py:19-28 agent, :69-77 ball): friction multiplier, max_velocity clamp */
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const bool ag = i < 4;
+        float vx = E.vx[i], vy = E.vy[i];
+        if (ag) { vx = vx + (Fx[i] * c.agent_minv) * DT; vy = vy + (Fy[i] * c.agent_minv) * DT; }
+        const float fr = ag ? c.agent_friction : c.ball_friction;
+        vx *= fr; vy *= fr;
+        if (ag) E.w[i] = (E.w[i] + (Tq[i] * c.agent_iinv) * DT) * fr;
+        const float l2 = vx * vx + vy * vy;
+        if (l2 > c.max_velocity * c.max_velocity) { const float s_ = c.max_velocity * rsqrt_f(l2); vx *= s_; vy *= s_; }
+        E.vx[i] = vx; E.vy[i] = vy;
+    }
+
+    if (contact_path) {
+        CacheIO cio;
+        cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
+        cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
+        cio.n = A.n; cio.e = e; cio.old_count = old_count;
+        if (W.nc > 0) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) { W.bvx[i] = E.vx[i]; W.bvy[i] = E.vy[i]; W.bw[i] = E.w[i]; }
+            /* ---- cpArbiterApplyCachedImpulse (skipped for arbiters in their first step) */
+            for (int k = 0; k < W.nc; k++) {
+                if ((W.meta[k] >> 16) & 1u) continue;
+                const int a = W.meta[k] & 7u, b = (W.meta[k] >> 3) & 7u;
+                const V2 n = mk(W.nx[k], W.ny[k]);
+                const V2 j = vrot(n, mk(W.jn[k], W.jt[k]));
+                const V2 r1 = mk(W.r1x[k], W.r1y[k]), r2 = mk(W.r2x[k], W.r2y[k]);
+                W.bvx[a] -= j.x * W.bmi[a]; W.bvy[a] -= j.y * W.bmi[a]; W.bw[a] -= W.bii[a] * vcross(r1, j);
+                W.bvx[b] += j.x * W.bmi[b]; W.bvy[b] += j.y * W.bmi[b]; W.bw[b] += W.bii[b] * vcross(r2, j);
+            }
+            /* ---- cpArbiterApplyImpulse x 10 */
+#pragma unroll 1
+            for (int it = 0; it < SOLVER_ITERS; it++) {
+#pragma unroll 1
+                for (int k = 0; k < W.nc; k++) {
+                    const int a = W.meta[k] & 7u, b = (W.meta[k] >> 3) & 7u;
+                    const V2 n = mk(W.nx[k], W.ny[k]);
+                    const V2 r1 = mk(W.r1x[k], W.r1y[k]), r2 = mk(W.r2x[k], W.r2y[k]);
+                    const float ma = W.bmi[a], ia = W.bii[a], mb = W.bmi[b], ib = W.bii[b];
+                    const V2 vb1 = mk(W.bbx[a], W.bby[a]) + vperp(r1) * W.bbw[a];
+                    const V2 vb2 = mk(W.bbx[b], W.bby[b]) + vperp(r2) * W.bbw[b];
+                    const V2 v1 = mk(W.bvx[a], W.bvy[a]) + vperp(r1) * W.bw[a];
+                    const V2 v2 = mk(W.bvx[b], W.bvy[b]) + vperp(r2) * W.bw[b];
+                    const V2 vr = v2 - v1;
+                    const float vbn = vdot(vb2 - vb1, n), vrn = vdot(vr, n), vrt = vdot(vr, vperp(n));
+                    const float jbn = (W.bias[k] - vbn) * W.nMass[k];
+                    const float jbnOld = W.jb[k];
+                    const float jbNew = fmaxf(jbnOld + jbn, 0.0f);
+                    const float jn = -(W.bounce[k] + vrn) * W.nMass[k];
+                    const float jnOld = W.jn[k];
+                    const float jnNew = fmaxf(jnOld + jn, 0.0f);
+                    const float jtMax = W.u[k] * jnNew;
+                    const float jt = -vrt * W.tMass[k];
+                    const float jtOld = W.jt[k];
+                    const float jtNew = fminf(fmaxf(jtOld + jt, -jtMax), jtMax);
+                    W.jb[k] = jbNew; W.jn[k] = jnNew; W.jt[k] = jtNew;
+                    const V2 jB = n * (jbNew - jbnOld);
+                    W.bbx[a] -= jB.x * ma; W.bby[a] -= jB.y * ma; W.bbw[a] -= ia * vcross(r1, jB);
+                    W.bbx[b] += jB.x * mb; W.bby[b] += jB.y * mb; W.bbw[b] += ib * vcross(r2, jB);
+                    const V2 j = vrot(n, mk(jnNew - jnOld, jtNew - jtOld));
+                    W.bvx[a] -= j.x * ma; W.bvy[a] -= j.y * ma; W.bw[a] -= ia * vcross(r1, j);
+                    W.bvx[b] += j.x * mb; W.bvy[b] += j.y * mb; W.bw[b] += ib * vcross(r2, j);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                E.vx[i] = W.bvx[i]; E.vy[i] = W.bvy[i]; E.w[i] = W.bw[i];
+                E.vbx[i] = W.bbx[i]; E.vby[i] = W.bby[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) E.wb[i] = W.bbw[i];
+        }
+
+        /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
+           arbiters younger than collision_persistence (3) */
+        for (int k = 0; k < W.nc && new_count < MAX_CACHE; k++) {
+            const int64_t o = (int64_t)new_count * A.n + e;
+            cio.new_info[o] = (W.meta[k] >> 6) & 1023u; /* pair | key<<6, age 0 */
+            cio.new_jn[o] = W.jn[k]; cio.new_jt[o] = W.jt[k];
+            new_count++;
+        }
+        for (int j = 0; j < old_count; j++) {
+            const int64_t oi = (int64_t)j * A.n + e;
+            const uint32_t info = cio.old_info[oi];
+            const uint32_t age = (info >> 10) & 3u;
+            if (((W.touched >> (info & 63u)) & 1ull) || age >= 2u) continue;
+            if (new_count >= MAX_CACHE) { overflow++; continue; }
+            const int64_t o = (int64_t)new_count * A.n + e;
+            cio.new_info[o] = (info & 1023u) | ((age + 1u) << 10);
+            cio.new_jn[o] = cio.old_jn[oi]; cio.new_jt[o] = cio.old_jt[oi];
+            new_count++;
+        }
+    }
+    E.flags = (E.flags & ~FLAG_CACHE_MASK) | (uint32_t)new_count;
+
+    /* ---- goal test (game/game.py:401-412), strict inequalities */
+    int goal = 0;
+    const float bx = E.px[4], by = E.py[4];
+    if (bx < FIELD_L && GOAL_Y_BOT < by && by < GOAL_Y_TOP) { goal = -1; E.score_r++; }
+    else if (bx > FIELD_R && GOAL_Y_BOT < by && by < GOAL_Y_TOP) { goal = +1; E.score_b++; }
+
+    /* ---- rewards (game/game.py:324-375) from the step displacement */
+    float r = 0.0f;
+    {
+        const float ibx = incx[4], iby = incy[4];
+        if (c.prox_mult != 0.0f) {
+            float imp = 0.0f;
+            {
+                const float lx = incx[0] - ibx, ly = incy[0] - iby;
+                const float dp = sqrtf(d0x * d0x + d0y * d0y);
+                const float nx_ = d0x + lx, ny_ = d0y + ly;
+                const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
+                const float den = dp + dc;
+                if (den > 0.0f) imp += -(2.0f * (d0x * lx + d0y * ly) + (lx * lx + ly * ly)) / den;
+            }
+            {
+                const float lx = incx[1] - ibx, ly = incy[1] - iby;
+                const float dp = sqrtf(d1x * d1x + d1y * d1y);
+                const float nx_ = d1x + lx, ny_ = d1y + ly;
+                const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
+                const float den = dp + dc;
+                if (den > 0.0f) imp += -(2.0f * (d1x * lx + d1y * ly) + (lx * lx + ly * ly)) / den;
+            }
+            r += c.prox_mult * imp;
+        }
+        {
+            const float dp = sqrtf(dgx * dgx + dgy * dgy);
+            const float nx_ = dgx + ibx, ny_ = dgy + iby;
+            const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
+            const float den = dp + dc;
+            float imp = 0.0f;
+            if (den > 0.0f) imp = -(2.0f * (dgx * ibx + dgy * iby) + (ibx * ibx + iby * iby)) / den;
+            r += imp * c.move_mult;
+        }
+        if (goal > 0) r += c.goal_reward;
+        if (goal < 0) r -= c.conceded_penalty;
+        r -= c.alive_penalty;
+    }
+
+    /* ---- soft reset on goal (game/game.py:421-422, :120-127): positions re-spawned in the current
+       mode, velocities zeroed, agent angles 0/pi; ball angular velocity, biases, counters kept */
+    if (goal != 0) {
+        uint32_t sc = A.spawn_count[e];
+        float px[5], py[5];
+        sc = spawn_positions((int)((E.flags & FLAG_MODE_MASK) >> FLAG_MODE_SHIFT), A.seed[e], gidx, sc, px, py);
+        A.spawn_count[e] = sc;
+#pragma unroll
+        for (int i = 0; i < 5; i++) { E.px[i] = px[i]; E.py[i] = py[i]; E.vx[i] = 0.0f; E.vy[i] = 0.0f; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) { E.w[i] = 0.0f; E.ang[i] = (i < 2) ? 0.0f : PI_F; }
+    }
+
+    /* ---- truncation at max_steps (game/game.py:424-433): reward replaced by the terminal bonus */
+    bool done = false;
+    if (c.max_steps > 0 && E.steps >= c.max_steps) {
+        done = true;
+        r = c.score_diff_mult * (float)(E.score_b - E.score_r);
+    }
+    E.ep_return += r;
+    out.reward = r; out.done = done ? 1 : 0; out.goal = (int8_t)goal;
+    out.fresh_episode = false; out.finished_return = 0.0f;
+    out.n_contacts = n_contacts; out.overflow = overflow;
+    out.score_b = E.score_b; out.score_r = E.score_r;
+    if (done) {
+        out.finished_return = E.ep_return;
+        E.ep_return = 0.0f;
+        if (step_flags & 1u) { /* marl_vecenv.py:45-53: auto-reset, full-random mode, no re-seed */
+            uint32_t sc = A.spawn_count[e];
+            env_full_reset(E, 2, A.seed[e], gidx, sc);
+            A.spawn_count[e] = sc;
+            out.fresh_episode = true;
+        }
+    }
+    make_frames<FSTRIDE>(E, c, frames);
+}
+
+} /* namespace msoc */

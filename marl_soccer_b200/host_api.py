@@ -1,0 +1,90 @@
+"""HostBufferSim -- the C-ABI of include/msoc.h driven with NumPy HOST buffers.
+
+This is the path the NumPy drop-in classes use (soccer_env.SoccerEnv, marl_vecenv.SyncMultiAgentVecEnv):
+actions are copied host->device, the fused kernel runs, observations / rewards / flags are copied back
+(msoc_step_host).  The simulation itself always runs on the GPU; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+class HostBufferSim:
+    def __init__(self, n: int, config: dict, seed: int = 0, global_offset: int = 0, device: int = 0):
+        self._L = _capi.lib()
+        self.n = int(n)
+        self.config = config
+        self._cfg = _capi.make_config(config)
+        h = C.c_void_p()
+        _capi.check(self._L.msoc_create(C.byref(self._cfg), self.n, int(device), int(seed) & (2**64 - 1),
+                                        int(global_offset), C.byref(h)))
+        self._h = h
+        self.score = np.zeros((self.n, 2), np.int32)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.msoc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self, mode: int = _capi.MODE_RANDOM, seed: int | None = None, mask=None) -> np.ndarray:
+        obs = np.zeros((self.n, 4, 66), np.float32)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        _capi.check(self._L.msoc_reset_host(self._h, None if m is None else m.ctypes.data, int(mode),
+                                            0 if seed is None else 1,
+                                            0 if seed is None else int(seed) & (2**64 - 1), obs.ctypes.data, None))
+        return obs
+
+    def step(self, actions, auto_reset: bool = True):
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 12)
+        obs = np.zeros((self.n, 4, 66), np.float32)
+        rew = np.zeros((self.n, 2), np.float32)
+        done = np.zeros(self.n, np.uint8)
+        goal = np.zeros(self.n, np.int8)
+        self.score = np.zeros((self.n, 2), np.int32)
+        _capi.check(self._L.msoc_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
+                                           done.ctypes.data, goal.ctypes.data, self.score.ctypes.data,
+                                           _capi.STEP_AUTO_RESET if auto_reset else 0, None))
+        return obs, rew, done, goal
+
+    def get_states(self, idx) -> list:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        arr = (_capi.MsocEnvState * len(idx))()
+        _capi.check(self._L.msoc_get_state(self._h, idx.ctypes.data, len(idx), C.byref(arr)))
+        return list(arr)
+
+    def set_states(self, idx, states, obs=None) -> None:
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        arr = (_capi.MsocEnvState * len(idx))(*states)
+        _capi.check(self._L.msoc_set_state(self._h, idx.ctypes.data, len(idx), C.byref(arr)))
+        if obs is not None:
+            o = np.ascontiguousarray(obs, dtype=np.float32).reshape(len(idx), 4, 66)
+            _capi.check(self._L.msoc_set_obs_host(self._h, idx.ctypes.data, len(idx), o.ctypes.data))
+
+    def get_state(self, i: int):
+        return self.get_states([i])[0]
+
+    def set_state(self, i: int, S, obs=None) -> None:
+        self.set_states([i], [S], None if obs is None else np.asarray(obs, np.float32)[None])
+
+    def get_obs(self, i: int) -> np.ndarray:
+        idx = np.array([i], np.int64)
+        o = np.zeros((1, 4, 66), np.float32)
+        _capi.check(self._L.msoc_get_obs_host(self._h, idx.ctypes.data, 1, o.ctypes.data))
+        return o[0]
+
+    def counters(self):
+        score = np.zeros((self.n, 2), np.int32)
+        steps = np.zeros((self.n,), np.int32)
+        _capi.check(self._L.msoc_read_counters(self._h, score.ctypes.data, steps.ctypes.data, None))
+        return score, steps
+
+    def stats(self, reset: bool = False) -> dict:
+        s = _capi.MsocStats()
+        _capi.check(self._L.msoc_stats_read(self._h, C.byref(s), 1 if reset else 0, None))
+        return {k: getattr(s, k) for k, _ in _capi.MsocStats._fields_}

@@ -1,0 +1,143 @@
+"""Parity of the CUDA kernels (through the C-ABI, include/msoc.h) with the CPU oracle.  -m gpu."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import parity_util as P
+
+pytestmark = pytest.mark.gpu
+
+
+def Dev(n, config, seed=0, global_offset=0):
+    from marl_soccer_b200.host_api import HostBufferSim
+    return HostBufferSim(n, config, seed=seed, global_offset=global_offset)
+
+
+def test_spawn_bit_exact_all_modes():
+    n = 4096
+    for mode in (O.MODE_RANDOM, O.MODE_FIXED, O.MODE_FULL_RANDOM):
+        sim = Dev(n, P.CONFIG, seed=5, global_offset=1000)
+        ora = O.OracleVec(n, P.CONFIG, seed=5, global_offset=1000)
+        o_d = sim.reset(mode, seed=77)
+        o_o = ora.reset(mode, seed=77)
+        idx = np.arange(0, n, 5)
+        for i, sd in zip(idx, sim.get_states(idx)):
+            so = ora.env(int(i)).get_state()
+            assert np.array_equal(np.array(sd.pos, np.float64), so["pos"]), (mode, i)
+            assert sd.spawn_count == so["spawn_count"] and sd.seed == so["seed"]
+        assert np.allclose(o_d, o_o, atol=P.ATOL["obs"])
+
+
+def test_single_step_injected_states_4096():
+    """BASELINE config 2: 4 096 batched envs, parity vs the restated Game on injected states."""
+    worst, goals = P.check_single_step(Dev, 4096, seed=11)
+    assert goals > 200
+    print("worst violation ratios", worst)
+
+
+def test_tracked_rollout_full_random_100_steps():
+    bad, total, ev, worst = P.check_tracked_rollout(Dev, 128, 100, seed=3, mode=O.MODE_FULL_RANDOM)
+    assert ev["dones"] > 0 and ev["contacts"] > 1000
+    assert bad <= total // 1000 + 1, (bad, total, worst)
+    print("tracked rollout", bad, total, ev, worst)
+
+
+def test_tracked_rollout_default_mode():
+    bad, total, ev, worst = P.check_tracked_rollout(Dev, 64, 60, seed=4, mode=O.MODE_RANDOM)
+    assert bad <= total // 1000 + 1, (bad, total, worst)
+
+
+def test_free_running_contact_free_100_steps():
+    n = 64
+    sim = Dev(n, P.CONFIG, seed=1)
+    ora = O.OracleVec(n, P.CONFIG, seed=1)
+    sim.reset(O.MODE_FIXED)
+    ora.reset(O.MODE_FIXED)
+    rng = np.random.default_rng(2)
+    for t in range(100):
+        act = (rng.uniform(-1, 1, (n, 4, 3)) * [0.02, 0.02, 1.0]).astype(np.float32)
+        o_d, r_d, d_d, g_d = sim.step(act, auto_reset=False)
+        o_o, r_o, d_o, g_o = ora.step(act, auto_reset=False)
+        assert np.array_equal(d_d, d_o) and np.array_equal(g_d, g_o)
+    worst, failing, cache_bad = P.compare_all(sim, ora, o_d, o_o, r_d, r_o, n)
+    assert not cache_bad
+    assert max(worst.values()) < 8.0, worst
+
+
+def test_global_offset_shards_agree():
+    full = Dev(4096, P.CONFIG, seed=9)
+    lo = Dev(2048, P.CONFIG, seed=9, global_offset=0)
+    hi = Dev(2048, P.CONFIG, seed=9, global_offset=2048)
+    a = full.reset(O.MODE_FULL_RANDOM, seed=123)
+    b = np.concatenate([lo.reset(O.MODE_FULL_RANDOM, seed=123), hi.reset(O.MODE_FULL_RANDOM, seed=123)])
+    assert np.array_equal(a, b)
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        act = rng.uniform(-1, 1, (4096, 4, 3)).astype(np.float32)
+        fa = full.step(act)
+        la, ha = lo.step(act[:2048]), hi.step(act[2048:])
+        for x, y, z in zip(fa, la, ha):
+            assert np.array_equal(x, np.concatenate([y, z]))
+
+
+def test_ragged_sizes_and_masked_reset():
+    """Env counts that are not multiples of the warp/block tile, and masked resets."""
+    for n in (1, 31, 33, 127, 129, 1000):
+        sim = Dev(n, P.CONFIG, seed=2)
+        ora = O.OracleVec(n, P.CONFIG, seed=2)
+        o_d, o_o = sim.reset(O.MODE_FULL_RANDOM, seed=5), ora.reset(O.MODE_FULL_RANDOM, seed=5)
+        assert np.allclose(o_d, o_o, atol=P.ATOL["obs"])
+        act = np.random.default_rng(n).uniform(-1, 1, (n, 4, 3)).astype(np.float32)
+        o_d, r_d, d_d, g_d = sim.step(act)
+        o_o, r_o, d_o, g_o = ora.step(act)
+        worst, failing, cache_bad = P.compare_all(sim, ora, o_d, o_o, r_d, r_o, n)
+        assert not cache_bad and not failing, (n, failing[:3])
+        mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+        m_d = sim.reset(O.MODE_RANDOM, mask=mask)
+        m_o = ora.reset(O.MODE_RANDOM, mask=mask)
+        keep = mask == 0
+        assert np.allclose(m_d[mask == 1], m_o[mask == 1], atol=P.ATOL["obs"])
+        assert np.array_equal(m_d[keep], o_d[keep])  # untouched envs keep their observation rows
+
+
+def test_full_size_invariants_65536():
+    """BASELINE config 3 size: properties that do not need the oracle at full size."""
+    import torch
+    from marl_soccer_b200.sim import BatchedSoccerSim
+    n = 65536
+    sim = BatchedSoccerSim(n, config=P.CONFIG, seed=0)
+    sim.reset(2, seed=0)
+    st = sim.get_states(np.arange(0, n, 997))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    prev = sim.obs.clone()
+    total_done = 0
+    # put every env 5 steps before truncation so that the auto-reset path runs at full size
+    some = sim.get_states(np.arange(n))
+    for s in some:
+        s.steps = 995
+    sim.set_states(np.arange(n), some)
+    for t in range(8):
+        act = torch.rand((n, 4, 3), generator=g, device="cuda") * 2 - 1
+        obs, rew, done, goal = sim.step(act)
+        obs_c = obs.clone()
+        assert torch.equal(rew[:, 0], rew[:, 1])
+        fresh = done.bool()
+        total_done += int(fresh.sum())
+        assert bool(((t == 4) == fresh).all()), "done <=> steps reached max_steps"
+        # frame shift: old frames 1,2 become frames 0,1 unless the env was auto-reset
+        keep = ~fresh
+        o4 = obs_c.view(n, 4, 3, 22)
+        p4 = prev.view(n, 4, 3, 22)
+        assert torch.equal(o4[keep][:, :, :2], p4[keep][:, :, 1:])
+        if fresh.any():
+            f = o4[fresh]
+            assert torch.equal(f[:, :, 0], f[:, :, 1]) and torch.equal(f[:, :, 1], f[:, :, 2])
+        # unit vectors have norm 1 (or 0)
+        u = o4[:, :, 2, 4:].reshape(n, 4, 6, 3)[..., :2]
+        nrm = (u * u).sum(-1).sqrt()
+        assert bool(((nrm - 1).abs() < 1e-5).logical_or(nrm == 0).all())
+        assert bool(torch.isfinite(obs_c).all())
+        prev = obs_c
+    assert total_done == n
+    stats = sim.stats()
+    assert stats["episodes"] == n and stats["env_steps"] == 8 * n and stats["contact_overflow"] == 0

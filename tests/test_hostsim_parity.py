@@ -1,0 +1,76 @@
+"""fp32 step arithmetic of the kernels (host build of step_core.cuh, tests/hostsim) against the fp64
+oracle.  Runs without a GPU; the same checks run on the real kernels in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import hostsim_lib as H
+import oracle_lib as O
+import parity_util as P
+
+P.add_batch_api(H.HostSim)
+
+
+def test_spawn_bit_exact_all_modes():
+    n = 512
+    for mode in (O.MODE_RANDOM, O.MODE_FIXED, O.MODE_FULL_RANDOM):
+        sim = H.HostSim(n, P.CONFIG, seed=5, global_offset=1000)
+        ora = O.OracleVec(n, P.CONFIG, seed=5, global_offset=1000)
+        o_d = sim.reset(mode, seed=77)
+        o_o = ora.reset(mode, seed=77)
+        for i in range(0, n, 7):
+            sd, so = sim.get_state(i), ora.env(i).get_state()
+            assert np.array_equal(np.array(sd.pos, np.float64), so["pos"]), (mode, i)
+            assert sd.spawn_count == so["spawn_count"] and sd.seed == so["seed"]
+        assert np.allclose(o_d, o_o, atol=P.ATOL["obs"])
+
+
+def test_single_step_injected_states():
+    worst, goals = P.check_single_step(H.HostSim, 1024, seed=11)
+    assert goals > 50  # the 'goal' scenario kind really crosses the line
+
+
+def test_tracked_rollout_full_random():
+    bad, total, ev, worst = P.check_tracked_rollout(H.HostSim, 48, 100, seed=3, mode=O.MODE_FULL_RANDOM)
+    assert ev["dones"] > 0 and ev["contacts"] > 500
+    assert bad <= total // 1000 + 1, (bad, total, worst)
+
+
+def test_tracked_rollout_default_mode():
+    bad, total, ev, worst = P.check_tracked_rollout(H.HostSim, 32, 60, seed=4, mode=O.MODE_RANDOM)
+    assert bad <= total // 1000 + 1, (bad, total, worst)
+
+
+def test_free_running_contact_free_100_steps():
+    """100-step free-running rollout (no re-synchronisation) from the fixed kickoff with small forces:
+    nobody touches anything, so fp32 and fp64 stay within the single-step tolerance bands."""
+    n = 8
+    sim = H.HostSim(n, P.CONFIG, seed=1)
+    ora = O.OracleVec(n, P.CONFIG, seed=1)
+    sim.reset(O.MODE_FIXED)
+    ora.reset(O.MODE_FIXED)
+    rng = np.random.default_rng(2)
+    for t in range(100):
+        act = (rng.uniform(-1, 1, (n, 4, 3)) * [0.02, 0.02, 1.0]).astype(np.float32)
+        o_d, r_d, d_d, g_d = sim.step(act, auto_reset=False)
+        o_o, r_o, d_o, g_o = ora.step(act, auto_reset=False)
+    worst, failing, cache_bad = P.compare_all(sim, ora, o_d, o_o, r_d, r_o, n)
+    assert not cache_bad
+    # 100 steps of accumulated rounding: allow 8x the single-step band
+    assert max(worst.values()) < 8.0, worst
+
+
+def test_global_offset_shards_agree():
+    """Env i of a 2-shard run equals env i of the 1-shard run (Philox keyed by the global env index)."""
+    full = H.HostSim(64, P.CONFIG, seed=9)
+    lo = H.HostSim(32, P.CONFIG, seed=9, global_offset=0)
+    hi = H.HostSim(32, P.CONFIG, seed=9, global_offset=32)
+    a = full.reset(O.MODE_FULL_RANDOM, seed=123)
+    b = np.concatenate([lo.reset(O.MODE_FULL_RANDOM, seed=123), hi.reset(O.MODE_FULL_RANDOM, seed=123)])
+    assert np.array_equal(a, b)
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        act = rng.uniform(-1, 1, (64, 4, 3)).astype(np.float32)
+        fa = full.step(act)
+        la, ha = lo.step(act[:32]), hi.step(act[32:])
+        for x, y, z in zip(fa, la, ha):
+            assert np.array_equal(x, np.concatenate([y, z]))
