@@ -26,7 +26,7 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 DEFAULT_ENVS_PER_GPU = 1_048_576  # BASELINE config 3 size; working set >> 126 MB L2
 WORKLOAD = ("2v2 soccer, {n} envs per GPU (BASELINE config-3 size on every GPU), config.json defaults, "
-            "random actions U(-1,1) from a pool of 16 device tensors, auto-reset in full-random mode, shaped "
+            "i.i.d. random actions U(-1,1) (random windows of a pre-generated device buffer), auto-reset in full-random mode, shaped "
             "rewards, episodes staggered over all phases")
 
 
@@ -57,10 +57,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
@@ -69,10 +69,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
@@ -93,11 +93,12 @@ def cpu_oracle_run(n_envs: int, steps: int, threads: int, seed: int = 0):
     vec = O.OracleVec(n_envs, O.DEFAULT_CONFIG, seed=seed)
     vec.reset(O.MODE_FULL_RANDOM, seed=seed)
     rng = np.random.default_rng(seed)
-    pool = [rng.uniform(-1, 1, (n_envs, 4, 3)).astype(np.float32) for _ in range(4)]
-    vec.step(pool[0], auto_reset=True, nthreads=threads)
+    flat = rng.uniform(-1, 1, 16 * n_envs * 12).astype(np.float32)  # i.i.d. windows, as on the GPU arm
+    offs = rng.integers(0, 15 * n_envs, size=steps + 1) * 12
+    vec.step(flat[offs[steps]:offs[steps] + n_envs * 12], auto_reset=True, nthreads=threads)
     t0 = time.perf_counter()
     for k in range(steps):
-        vec.step(pool[k % 4], auto_reset=True, nthreads=threads)
+        vec.step(flat[offs[k]:offs[k] + n_envs * 12], auto_reset=True, nthreads=threads)
     dt = time.perf_counter() - t0
     return n_envs * steps / dt, dt
 
@@ -172,8 +173,20 @@ def main():
     L = _capi.lib()
     sim = BatchedSoccerSim(n, config=cfg, device=dev, seed=0, global_env_offset=rank * n)
     sim.reset(_capi.MODE_FULL_RANDOM, seed=0)
+    # Actions: one flat device buffer of 16*N*12 uniform(-1,1) floats generated before the timed region;
+    # step k reads the window starting at a pseudo-random env offset r_k, so every env sees an
+    # effectively i.i.d. action stream (a plain cycle over 16 tensors would give each env a periodic
+    # sequence with a constant net drift, pinning the agents against the walls).
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    pool = [torch.rand((n, 4, 3), generator=gen, device=dev) * 2 - 1 for _ in range(16)]
+    POOL = 16
+    flat = torch.rand((POOL * n * 12,), generator=gen, device=dev) * 2 - 1
+    offs = np.random.default_rng(99 + rank).integers(0, (POOL - 1) * n, size=1 << 16)
+
+    class _Pool:
+        def __getitem__(self, k):
+            o = int(offs[k % len(offs)]) * 12
+            return flat[o:o + n * 12].view(n, 4, 3)
+    pool = _Pool()
 
     # pre-roll (untimed): env i is re-spawned at pre-roll step hash(i) % max_steps, so after one episode
     # length the episode phases are uniformly staggered and any timed window sees the time-average mix of
@@ -182,9 +195,9 @@ def main():
     phase = (torch.arange(n, device=dev, dtype=torch.int64) * 2654435761) % max_steps
     for k in range(args.preroll):
         sim.reset(_capi.MODE_FULL_RANDOM, mask=(phase == (k % max_steps)))
-        sim.step(pool[k % 16])
+        sim.step(pool[k])
     for k in range(max(3, args.warmup)):
-        sim.step(pool[k % 16])
+        sim.step(pool[args.preroll + k])
     sim.stats(reset=True)
     torch.cuda.synchronize(dev)
 
@@ -197,8 +210,9 @@ def main():
     launches0 = L.msoc_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    base_k = args.preroll + max(3, args.warmup)
     for k in range(args.steps):
-        sim.step(pool[k % 16])
+        sim.step(pool[base_k + k])
     stats_t = sim.stats_tensor(reset=False)
     if dist is not None:
         dist.all_reduce(stats_t)  # the only collective: one 64-byte sum per rollout
@@ -224,6 +238,7 @@ def main():
     import ctypes as C
     h_act = torch.empty((n, 4, 3), dtype=torch.float32).pin_memory()
     h_act.copy_(pool[0].cpu())
+    h_acts = [h_act] + [torch.empty((n, 4, 3), dtype=torch.float32).pin_memory().copy_(pool[7 + j].cpu()) for j in range(3)]
     h_obs = torch.empty((n, 4, 66), dtype=torch.float32).pin_memory()
     h_rew = torch.empty((n, 2), dtype=torch.float32).pin_memory()
     h_done = torch.empty((n,), dtype=torch.uint8).pin_memory()
@@ -231,8 +246,8 @@ def main():
     h_score = torch.empty((n, 2), dtype=torch.int32).pin_memory()
     stream = torch.cuda.current_stream(dev).cuda_stream
 
-    def host_step():
-        _capi.check(L.msoc_step_host(sim._h, h_act.data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(), h_done.data_ptr(),
+    def host_step(j=0):
+        _capi.check(L.msoc_step_host(sim._h, h_acts[j % 4].data_ptr(), h_obs.data_ptr(), h_rew.data_ptr(), h_done.data_ptr(),
                                      h_goal.data_ptr(), h_score.data_ptr(), _capi.STEP_AUTO_RESET, stream))
     for _ in range(3):
         host_step()
@@ -240,8 +255,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        host_step()
+    for j in range(args.e2e_steps):
+        host_step(j)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

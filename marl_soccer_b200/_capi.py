@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmsoc.so")
+LIB_PATH = os.environ.get("MSOC_LIB", os.path.join(PKG_DIR, "libmsoc.so"))  # MSOC_LIB: kernel A/B experiments
 
 N_AGENTS, ACT_DIM, FRAME, STACK, OBS, MAX_CACHE = 4, 3, 22, 3, 66, 32
 MODE_RANDOM, MODE_FIXED, MODE_FULL_RANDOM = 0, 1, 2

@@ -57,6 +57,7 @@ struct msoc_handle {
     SimCfg cfg;
     Arrays A;
     int cur; /* which half of the ping-pong arbiter cache is current */
+    int sm_count, blocks_per_sm; /* persistent grid of the step kernel */
     void *slab;
     /* internal I/O buffers of the host-buffer API */
     float *d_obs, *d_act, *d_rew;
@@ -68,50 +69,62 @@ struct msoc_handle {
 };
 
 constexpr int WARPS_PER_BLOCK = 4;
-constexpr int BLOCK = WARPS_PER_BLOCK * 32;
+constexpr int BLOCK = WARPS_PER_BLOCK * 32; /* reset kernel */
+constexpr int STEP_BLOCK = 128;             /* step kernel: envs (= threads) per block */
+#ifndef MSOC_STEP_MIN_BLOCKS
+#define MSOC_STEP_MIN_BLOCKS 3
+#endif
+constexpr int STEP_MIN_BLOCKS = MSOC_STEP_MIN_BLOCKS; /* resident blocks per SM the register budget is set for */
+
+/* ------------------------------------------------------------------ coalesced observation rows */
 constexpr int ENV_STRIDE = 89; /* floats of shared memory per env for the 4 new frames (odd: no bank conflicts) */
 
-/* ------------------------------------------------------------------ coalesced observation tile */
-/* One warp writes the stacked observations of its 32 envs (33 792 contiguous bytes).  Row r = env*4 +
-   agent holds 33 float2: [frame t-2 | frame t-1 | frame t].  Frames t-2, t-1 come from obs_in shifted
-   by one frame (soccer_env.py:134-137), frame t from shared memory; envs in fresh_mask (reset or
-   auto-reset, soccer_env.py:92-96) get three copies of the new frame.  Safe when obs_out == obs_in:
-   within a batch of rows all loads precede all stores. */
-__device__ __forceinline__ void write_obs_tile(const float *obs_in, float *obs_out, const float *s_new,
-                                               uint32_t write_mask, uint32_t fresh_mask, int64_t env_base, int lane)
+/* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns the env
+   with block-local index `my_local` (envs need not be consecutive); `in2` / `out2` point at the block's
+   first env.  An env's 4 rows are 1 056 contiguous, 32-byte aligned bytes = 132 float2; row = 33 float2:
+   [frame t-2 | frame t-1 | frame t].  Frames t-2, t-1 come from obs_in shifted by one frame
+   (soccer_env.py:134-137), frame t from shared memory (lane l's 4 frames at s_new + l*ENV_STRIDE); envs
+   in `fresh` (reset / auto-reset, soccer_env.py:92-96) get three copies of the new frame.  Safe when
+   obs_out == obs_in: within a batch of rows all loads precede all stores, and one env's rows are only
+   ever touched by the warp that owns it. */
+__device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, const float *s_new, uint32_t mask,
+                                               uint32_t fresh, int64_t my_env, int lane)
 {
     const int f_lane = lane / 11, j_lane = lane - f_lane * 11;
-    const float2 *in2 = reinterpret_cast<const float2 *>(obs_in) + env_base * 132;
-    float2 *out2 = reinterpret_cast<float2 *>(obs_out) + env_base * 132;
-    constexpr int RB = 8;
+    constexpr int RB = 8; /* rows per batch = 2 envs */
 #pragma unroll 1
-    for (int r0 = 0; r0 < 128; r0 += RB) {
+    for (int l0 = 0; l0 < 32; l0 += 2) {
+        const uint32_t m2 = (mask >> l0) & 3u;
+        if (m2 == 0u) continue;
+        const int64_t base0 = __shfl_sync(0xffffffffu, my_env, l0) * 132;
+        const int64_t base1 = __shfl_sync(0xffffffffu, my_env, l0 + 1) * 132;
         float2 v[RB];
 #pragma unroll
         for (int u = 0; u < RB; u++) {
-            const int r = r0 + u, e = r >> 2, a = r & 3;
-            if (!((write_mask >> e) & 1u)) continue;
-            if (f_lane == 2 || ((fresh_mask >> e) & 1u)) {
-                const float *s = s_new + e * ENV_STRIDE + a * 22 + 2 * j_lane;
-                v[u] = make_float2(s[0], s[1]);
+            const int l = l0 + (u >> 2), a = u & 3;
+            if (!((m2 >> (u >> 2)) & 1u)) continue;
+            const int64_t row = ((u >> 2) ? base1 : base0) + a * 33;
+            if (f_lane == 2 || ((fresh >> l) & 1u)) {
+                const float *sp = s_new + l * ENV_STRIDE + a * 22 + 2 * j_lane;
+                v[u] = make_float2(sp[0], sp[1]);
             } else {
-                v[u] = in2[r * 33 + lane + 11];
+                v[u] = in2[row + lane + 11];
             }
         }
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < RB; u++) {
-            const int r = r0 + u, e = r >> 2;
-            if ((write_mask >> e) & 1u) out2[r * 33 + lane] = v[u];
+            if (!((m2 >> (u >> 2)) & 1u)) continue;
+            const int64_t row = ((u >> 2) ? base1 : base0) + (u & 3) * 33;
+            out2[row + lane] = v[u];
         }
     }
-    /* last float2 of every row (frame t, floats 20-21) */
+    /* last float2 of every row (frame t, floats 20-21): lane l writes its own env's four */
+    if ((mask >> lane) & 1u) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int r = lane + 32 * i, e = r >> 2, a = r & 3;
-        if ((write_mask >> e) & 1u) {
-            const float *s = s_new + e * ENV_STRIDE + a * 22 + 20;
-            out2[r * 33 + 32] = make_float2(s[0], s[1]);
+        for (int a = 0; a < 4; a++) {
+            const float *sp = s_new + lane * ENV_STRIDE + a * 22 + 20;
+            out2[my_env * 132 + a * 33 + 32] = make_float2(sp[0], sp[1]);
         }
     }
 }
@@ -133,57 +146,118 @@ struct StepParams {
     int cur;
 };
 
-__global__ void __launch_bounds__(BLOCK, 4) msoc_step_kernel(const __grid_constant__ StepParams P)
-{
-    __shared__ float s_frames[WARPS_PER_BLOCK][32 * ENV_STRIDE];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t env_base = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 32;
-    const int64_t e = env_base + lane;
-    const bool active = e < P.A.n;
-    if (env_base >= P.A.n) return; /* whole warp out of range */
+/* Per-thread tallies for the per-rollout statistics. */
+struct Tally { int done, goals_b, goals_r, contacts, overflow, envs; float ret; };
 
+__device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &P, int64_t e, Env &E, Work &W, int &load, bool &fresh,
+                                             Tally &T)
+{
+    float act[12];
+    const float4 *a4 = reinterpret_cast<const float4 *>(P.actions + e * 12);
+    const float4 x0 = __ldg(a4), x1 = __ldg(a4 + 1), x2 = __ldg(a4 + 2);
+    act[0] = x0.x; act[1] = x0.y; act[2] = x0.z; act[3] = x0.w;
+    act[4] = x1.x; act[5] = x1.y; act[6] = x1.z; act[7] = x1.w;
+    act[8] = x2.x; act[9] = x2.y; act[10] = x2.z; act[11] = x2.w;
+    load_env(P.A, e, E);
     StepOut out;
-    out.reward = 0.0f; out.done = 0; out.goal = 0; out.fresh_episode = false; out.finished_return = 0.0f;
-    out.n_contacts = 0; out.overflow = 0; out.score_b = 0; out.score_r = 0;
-    if (active) {
-        float act[12];
-        const float4 *a4 = reinterpret_cast<const float4 *>(P.actions + e * 12);
-        const float4 x0 = __ldg(a4), x1 = __ldg(a4 + 1), x2 = __ldg(a4 + 2);
-        act[0] = x0.x; act[1] = x0.y; act[2] = x0.z; act[3] = x0.w;
-        act[4] = x1.x; act[5] = x1.y; act[6] = x1.z; act[7] = x1.w;
-        act[8] = x2.x; act[9] = x2.y; act[10] = x2.z; act[11] = x2.w;
-        Env E;
-        load_env(P.A, e, E);
-        env_step<22>(E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags,
-                     &s_frames[warp][lane * ENV_STRIDE], out);
-        store_env(P.A, e, E);
-        reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
-        P.done[e] = out.done;
-        P.goal[e] = out.goal;
-        if (P.score != nullptr) reinterpret_cast<int2 *>(P.score)[e] = make_int2(out.score_b, out.score_r);
+    if (!env_step(FAST, E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
+    store_env(P.A, e, E);
+    reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
+    P.done[e] = out.done;
+    P.goal[e] = out.goal;
+    if (P.score != nullptr) reinterpret_cast<int2 *>(P.score)[e] = make_int2(out.score_b, out.score_r);
+    fresh = out.fresh_episode;
+    T.done += out.done; T.goals_b += out.goal > 0; T.goals_r += out.goal < 0; T.envs += 1;
+    T.contacts += out.n_contacts; T.overflow += out.overflow; T.ret += out.finished_return;
+    return true;
+}
+
+/* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
+   lanes' solver bodies (30 fields) and first CON_FAST contacts (56 fields), field-major with stride 32
+   (conflict-free); afterwards the lanes' four new observation frames (lane-major, stride ENV_STRIDE). */
+static_assert(BODY_FIELDS * 5 + CON_FIELDS * CON_FAST <= ENV_STRIDE, "solver scratch must fit the frame staging");
+constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
+
+/* The fused step: a persistent grid (a few blocks per SM) walks over tiles of STEP_BLOCK consecutive envs.
+   tile round     thread t steps env tile*STEP_BLOCK + t in contact-free mode and its warp writes those
+                  envs' observation rows; envs whose broad phase found a candidate pair (or that still
+                  carry cached arbiters) decline and are pushed to a block-local queue in shared memory;
+   contact round  as soon as the queue holds STEP_BLOCK envs (or the tiles are exhausted) every thread
+                  pops one and steps it in full mode (narrow phase, arbiter cache, 10-iteration impulse
+                  solver with bodies and contacts in shared memory) and its warp writes the rows.
+   The divergent, latency-bound contact work therefore always runs on full warps, all warps of a block
+   stay busy, and a single copy of the step code serves both kinds of round. */
+constexpr int QUEUE_CAP = 2 * STEP_BLOCK;
+
+__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(const __grid_constant__ StepParams P)
+{
+    extern __shared__ float s_dyn[];
+    __shared__ int s_queue[QUEUE_CAP];
+    __shared__ int s_qtail; /* total pushed (monotonic) */
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
+    const int64_t n_tiles = (P.A.n + STEP_BLOCK - 1) / STEP_BLOCK;
+    const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
+    float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
+    if (tid == 0) s_qtail = 0;
+    __syncthreads();
+
+    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    Work W;
+    W.body = s_warp + lane; W.bstride = 32;
+    W.con = s_warp + BODY_FIELDS * 5 * 32 + lane; W.cstride = 32;
+    int64_t tile = blockIdx.x;
+    int qhead = 0; /* total popped (block-uniform) */
+#pragma unroll 1
+    while (true) {
+        const int qcount = s_qtail - qhead; /* block-uniform: nobody pushes between the two barriers around this read */
+        __syncthreads();
+        const bool tiles_left = tile < n_tiles;
+        const bool contact_round = qcount >= STEP_BLOCK || (!tiles_left && qcount > 0);
+        if (!contact_round && !tiles_left) break;
+        int64_t my_env;
+        bool have;
+        if (contact_round) {
+            const int take = qcount < STEP_BLOCK ? qcount : STEP_BLOCK;
+            have = tid < take;
+            my_env = have ? (int64_t)s_queue[(qhead + tid) % QUEUE_CAP] : 0;
+            qhead += take;
+        } else {
+            my_env = tile * STEP_BLOCK + tid;
+            have = my_env < P.A.n;
+            tile += gridDim.x;
+        }
+        bool fresh = false, ok = false;
+        int load = 0;
+        {
+            Env E;
+            if (have) ok = step_one_env(!contact_round, P, my_env, E, W, load, fresh, T);
+            __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
+            if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
+        __syncwarp();
+        if (mask) write_obs_tile(in2, out2, s_warp, mask, fmask, my_env, lane);
+        if (have && !ok) s_queue[atomicAdd(&s_qtail, 1) % QUEUE_CAP] = (int)my_env;
+        __syncthreads();
     }
-    const uint32_t write_mask = __ballot_sync(0xffffffffu, active);
-    const uint32_t fresh_mask = __ballot_sync(0xffffffffu, active && out.fresh_episode);
-    __syncwarp();
-    write_obs_tile(P.obs_in, P.obs_out, s_frames[warp], write_mask, fresh_mask, env_base, lane);
 
     /* per-rollout statistics (marl-soccer.ipynb:411-429): warp reduce, one atomic per warp and counter */
-    const uint32_t done_mask = __ballot_sync(0xffffffffu, out.done != 0);
-    const uint32_t gb_mask = __ballot_sync(0xffffffffu, out.goal > 0);
-    const uint32_t gr_mask = __ballot_sync(0xffffffffu, out.goal < 0);
-    int nc = out.n_contacts, ov = out.overflow;
-    float ret = out.finished_return;
+    int nd = T.done, gb = T.goals_b, gr = T.goals_r, nc = T.contacts, ov = T.overflow, na = T.envs;
+    float ret = T.ret;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        nc += __shfl_xor_sync(0xffffffffu, nc, o);
-        ov += __shfl_xor_sync(0xffffffffu, ov, o);
+        nd += __shfl_xor_sync(0xffffffffu, nd, o); gb += __shfl_xor_sync(0xffffffffu, gb, o);
+        gr += __shfl_xor_sync(0xffffffffu, gr, o); nc += __shfl_xor_sync(0xffffffffu, nc, o);
+        ov += __shfl_xor_sync(0xffffffffu, ov, o); na += __shfl_xor_sync(0xffffffffu, na, o);
         ret += __shfl_xor_sync(0xffffffffu, ret, o);
     }
     if (lane == 0) {
-        if (done_mask) { atomicAdd(P.stats + 0, (double)__popc(done_mask)); atomicAdd(P.stats + 1, (double)ret); }
-        if (gb_mask) atomicAdd(P.stats + 2, (double)__popc(gb_mask));
-        if (gr_mask) atomicAdd(P.stats + 3, (double)__popc(gr_mask));
-        atomicAdd(P.stats + 4, (double)__popc(write_mask));
+        if (nd) { atomicAdd(P.stats + 0, (double)nd); atomicAdd(P.stats + 1, (double)ret); }
+        if (gb) atomicAdd(P.stats + 2, (double)gb);
+        if (gr) atomicAdd(P.stats + 3, (double)gr);
+        if (na) atomicAdd(P.stats + 4, (double)na);
         if (nc) atomicAdd(P.stats + 5, (double)nc);
         if (ov) atomicAdd(P.stats + 6, (double)ov);
     }
@@ -203,9 +277,9 @@ __global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant
 {
     __shared__ float s_frames[WARPS_PER_BLOCK][32 * ENV_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t env_base = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + warp) * 32;
-    const int64_t e = env_base + lane;
-    if (env_base >= P.A.n) return;
+    const int64_t block_base = (int64_t)blockIdx.x * BLOCK;
+    const int64_t e = block_base + threadIdx.x;
+    if (block_base + warp * 32 >= P.A.n) return;
     const bool doit = (e < P.A.n) && (P.mask == nullptr || P.mask[e] != 0);
     if (doit) {
         const uint64_t gidx = P.global_offset + (uint64_t)e;
@@ -220,7 +294,10 @@ __global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant
     }
     const uint32_t m = __ballot_sync(0xffffffffu, doit);
     __syncwarp();
-    if (P.obs_out != nullptr && m != 0u) write_obs_tile(P.obs_out, P.obs_out, s_frames[warp], m, m, env_base, lane);
+    if (P.obs_out != nullptr && m != 0u) {
+        float2 *o2 = reinterpret_cast<float2 *>(P.obs_out);
+        write_obs_tile(o2, o2, s_frames[warp], m, m, e, lane);
+    }
 }
 
 /* -------------------------------------------------------------------- state inject / extract */
@@ -374,6 +451,14 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     h->d_score = (int32_t *)(base + o_score);
     h->d_stats = (double *)(base + o_stats);
 
+    ce = cudaFuncSetAttribute(msoc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)STEP_SMEM_BYTES);
+    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_kernel, STEP_BLOCK, STEP_SMEM_BYTES);
+    if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) {
+        cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
+    }
     msoc_init_kernel<<<(unsigned)((n_envs + 255) / 256), 256>>>(A, seed);
     g_launches++;
     /* Game.__init__ -> setup_field -> reset(): first spawn in the default random mode */
@@ -420,7 +505,10 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_in = d_obs_in; P.obs_out = d_obs_out;
     P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
     P.global_offset = h->global_offset; P.flags = flags; P.cur = h->cur;
-    msoc_step_kernel<<<grid_for(h->n), BLOCK, 0, (cudaStream_t)stream>>>(P);
+    const int64_t n_tiles = (h->n + STEP_BLOCK - 1) / STEP_BLOCK;
+    const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
+    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    msoc_step_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     g_launches++;
     h->cur ^= 1;
     CUDA_TRY(cudaGetLastError());

@@ -27,6 +27,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MSOC_HD __host__ __device__ __forceinline__
@@ -302,6 +303,75 @@ MSOC_HD void make_frames(const Env &E, const SimCfg &c, float *out)
     }
 }
 
+/* One agent's frame (22 floats); same values as make_frames, used by the kernels to stage the
+   observation write agent by agent (pair vectors are recomputed instead of kept in registers). */
+template <int I>
+MSOC_HD void make_frame_agent(const Env &E, const SimCfg &c, float *o)
+{
+    const float vmax = fmaxf(c.max_velocity, 1e-6f), wmax = fmaxf(c.max_ang_vel, 1e-6f);
+    o[0] = E.vx[I] / vmax;
+    o[1] = E.vy[I] / vmax;
+    o[2] = E.ang[I] / PI_F;
+    o[3] = E.w[I] / wmax;
+    constexpr int MATE = (I == 0) ? 1 : (I == 1) ? 0 : (I == 2) ? 3 : 2;
+    constexpr int OPP0 = (I < 2) ? 2 : 0, OPP1 = (I < 2) ? 3 : 1;
+    /* mirror make_frames exactly: pair (lo, hi) is computed as hi - lo and negated for hi's frame */
+    {
+        float ux, uy, m;
+        constexpr int LO = I < MATE ? I : MATE, HI = I < MATE ? MATE : I;
+        unit_mag(E.px[HI] - E.px[LO], E.py[HI] - E.py[LO], ux, uy, m);
+        o[4] = (I == LO) ? ux : -ux; o[5] = (I == LO) ? uy : -uy; o[6] = m;
+    }
+    {
+        float ux, uy, m;
+        constexpr int LO = I < OPP0 ? I : OPP0, HI = I < OPP0 ? OPP0 : I;
+        unit_mag(E.px[HI] - E.px[LO], E.py[HI] - E.py[LO], ux, uy, m);
+        o[7] = (I == LO) ? ux : -ux; o[8] = (I == LO) ? uy : -uy; o[9] = m;
+    }
+    {
+        float ux, uy, m;
+        constexpr int LO = I < OPP1 ? I : OPP1, HI = I < OPP1 ? OPP1 : I;
+        unit_mag(E.px[HI] - E.px[LO], E.py[HI] - E.py[LO], ux, uy, m);
+        o[10] = (I == LO) ? ux : -ux; o[11] = (I == LO) ? uy : -uy; o[12] = m;
+    }
+    unit_mag(E.px[4] - E.px[I], E.py[4] - E.py[I], o[13], o[14], o[15]);
+    constexpr float own_x = (I < 2) ? FIELD_L : FIELD_R, opp_x = (I < 2) ? FIELD_R : FIELD_L;
+    unit_mag(own_x - E.px[I], 300.0f - E.py[I], o[16], o[17], o[18]);
+    unit_mag(opp_x - E.px[I], 300.0f - E.py[I], o[19], o[20], o[21]);
+}
+
+/* Frame of agent `a` (runtime index) from an env snapshot stored field-major with stride `st`:
+   snap[(f)*st], f = 0-4 px, 5-9 py, 10-13 vx, 14-17 vy, 18-21 angle, 22-25 angular velocity.
+   Same arithmetic as make_frames (u(p_j - p_i) = -u(p_i - p_j) exactly). */
+constexpr int SNAP_FIELDS = 26;
+MSOC_HD void snapshot_env(const Env &E, float *snap, int st)
+{
+#pragma unroll
+    for (int i = 0; i < 5; i++) { snap[i * st] = E.px[i]; snap[(5 + i) * st] = E.py[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        snap[(10 + i) * st] = E.vx[i]; snap[(14 + i) * st] = E.vy[i];
+        snap[(18 + i) * st] = E.ang[i]; snap[(22 + i) * st] = E.w[i];
+    }
+}
+MSOC_HD void make_frame_dyn(const float *snap, int st, int a, const SimCfg &c, float *o)
+{
+    const float vmax = fmaxf(c.max_velocity, 1e-6f), wmax = fmaxf(c.max_ang_vel, 1e-6f);
+    const float x = snap[a * st], y = snap[(5 + a) * st];
+    o[0] = snap[(10 + a) * st] / vmax;
+    o[1] = snap[(14 + a) * st] / vmax;
+    o[2] = snap[(18 + a) * st] / PI_F;
+    o[3] = snap[(22 + a) * st] / wmax;
+    const int opp0 = (a < 2) ? 2 : 0;
+    const int tgt[4] = {a ^ 1, opp0, opp0 + 1, 4};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        unit_mag(snap[tgt[k] * st] - x, snap[(5 + tgt[k]) * st] - y, o[4 + 3 * k], o[5 + 3 * k], o[6 + 3 * k]);
+    const float own_x = (a < 2) ? FIELD_L : FIELD_R, opp_x = (a < 2) ? FIELD_R : FIELD_L;
+    unit_mag(own_x - x, 300.0f - y, o[16], o[17], o[18]);
+    unit_mag(opp_x - x, 300.0f - y, o[19], o[20], o[21]);
+}
+
 /* ------------------------------------------------------------------------------------ narrow phase */
 struct Manifold { int count; V2 n; V2 p1[2], p2[2]; int key[2]; };
 struct Edge { V2 pa, pb; int ia, ib; float r; };
@@ -522,16 +592,41 @@ MSOC_HD void collide_ball_segment(const Seg &g, V2 c, Manifold &m)
 }
 
 /* ---------------------------------------------------------------------------------- solver storage */
-/* Per-thread scratch with dynamic indexing (local memory in v1). */
+/* Scratch of the contact path with dynamic indexing.  In the kernel `body` and `con` point into shared
+   memory (conflict-free: element (field, index) of thread t lives at (field*K + index)*stride + t), the
+   first CON_FAST contacts of an env are kept there and the rare further ones in the per-thread overflow
+   array (local memory).  In tests/hostsim both are plain arrays with stride 1. */
+constexpr int CON_FAST = 4;    /* contacts per env held in shared memory */
+constexpr int CON_FIELDS = 14; /* r1x r1y r2x r2y nx ny nMass tMass bounce bias jn jt jb meta */
+constexpr int BODY_FIELDS = 6; /* vx vy w bias_x bias_y bias_w, for the 5 dynamic bodies */
+enum { CF_R1X, CF_R1Y, CF_R2X, CF_R2Y, CF_NX, CF_NY, CF_NMASS, CF_TMASS, CF_BOUNCE, CF_BIAS, CF_JN, CF_JT, CF_JB, CF_META };
+enum { BF_VX, BF_VY, BF_W, BF_BX, BF_BY, BF_BW };
+
+MSOC_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+MSOC_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
 struct Work {
-    /* solver bodies; index 5 = the static body (inverse mass 0) */
-    float bvx[6], bvy[6], bw[6], bbx[6], bby[6], bbw[6], bmi[6], bii[6];
-    /* contacts */
-    float r1x[MAXC], r1y[MAXC], r2x[MAXC], r2y[MAXC], nx[MAXC], ny[MAXC];
-    float nMass[MAXC], tMass[MAXC], bounce[MAXC], bias[MAXC], jn[MAXC], jt[MAXC], jb[MAXC], u[MAXC];
-    uint32_t meta[MAXC]; /* a | b<<3 | pair<<6 | key<<12 | first<<16 */
+    float *body; int bstride;
+    float *con; int cstride;
+    float ovf[CON_FIELDS][MAXC - CON_FAST];
     int nc, overflow;
     uint64_t touched;
+    MSOC_HD float &B(int f, int i) { return body[(f * 5 + i) * bstride]; }
+    MSOC_HD float &C(int f, int k) { return k < CON_FAST ? con[(f * CON_FAST + k) * cstride] : ovf[f][k - CON_FAST]; }
 };
 
 struct CacheIO {
@@ -541,9 +636,18 @@ struct CacheIO {
     int old_count;
 };
 
+/* friction product of a pair id (cpArbiterUpdate u = ua*ub) */
+MSOC_HD float pair_friction(int pair)
+{
+    if (pair < PAIR_AGENT_AGENT) return ((pair & 7) < 6) ? U_AGENT_WALL : U_AGENT_GOALLINE;
+    if (pair < PAIR_BALL_AGENT) return U_AGENT_AGENT;
+    if (pair < PAIR_BALL_WALL) return U_BALL_AGENT;
+    return U_BALL_WALL;
+}
+
 /* cpSpaceCollideShapes + cpArbiterUpdate for one touching pair: append the manifold's contacts,
    carry jnAcc/jtAcc of equal-key contacts from the cache, decide first-contact state. */
-MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, float u, const Manifold &m,
+MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, const Manifold &m,
                           V2 r1_off, V2 r2_off)
 {
     W.touched |= (1ull << pair);
@@ -563,24 +667,40 @@ MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, f
         const int k = W.nc++;
         const V2 p1 = (i == 0) ? m.p1[0] : m.p1[1], p2 = (i == 0) ? m.p2[0] : m.p2[1];
         const int key = (i == 0) ? m.key[0] : m.key[1];
-        W.r1x[k] = p1.x - r1_off.x; W.r1y[k] = p1.y - r1_off.y;
-        W.r2x[k] = p2.x - r2_off.x; W.r2y[k] = p2.y - r2_off.y;
-        W.nx[k] = m.n.x; W.ny[k] = m.n.y;
-        W.jn[k] = (i == 0) ? cjn[0] : cjn[1];
-        W.jt[k] = (i == 0) ? cjt[0] : cjt[1];
-        W.jb[k] = 0.0f;
-        W.u[k] = u;
-        W.bounce[k] = e; /* restitution until the pre-step turns it into the bounce velocity */
+        W.C(CF_R1X, k) = p1.x - r1_off.x; W.C(CF_R1Y, k) = p1.y - r1_off.y;
+        W.C(CF_R2X, k) = p2.x - r2_off.x; W.C(CF_R2Y, k) = p2.y - r2_off.y;
+        W.C(CF_NX, k) = m.n.x; W.C(CF_NY, k) = m.n.y;
+        W.C(CF_JN, k) = (i == 0) ? cjn[0] : cjn[1];
+        W.C(CF_JT, k) = (i == 0) ? cjt[0] : cjt[1];
+        W.C(CF_JB, k) = 0.0f;
+        W.C(CF_BOUNCE, k) = e; /* restitution until the pre-step turns it into the bounce velocity */
         /* signed separation along n from the contact points themselves (translation invariant):
            cpArbiterPreStep dist = ((r2 - r1) + (pb - pa)) . n */
-        W.bias[k] = vdot(p2 - p1, m.n);
-        W.meta[k] = (uint32_t)a | ((uint32_t)b << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16);
+        W.C(CF_BIAS, k) = vdot(p2 - p1, m.n);
+        W.C(CF_META, k) = u2f((uint32_t)a | ((uint32_t)b << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16));
     }
 }
 
 MSOC_HD bool bb_overlap(float cx, float cy, float R, float l, float b, float r, float t)
 {
     return (cx - R <= r) && (l <= cx + R) && (cy - R <= t) && (b <= cy + R);
+}
+
+MSOC_HD int ctz32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+MSOC_HD int popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
 }
 
 /* ------------------------------------------------------------------------------------------ step */
@@ -611,9 +731,18 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
     E.flags = ((uint32_t)mode << FLAG_MODE_SHIFT); /* cache count 0, no bias */
 }
 
-template <int FSTRIDE>
-MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e, uint64_t gidx,
-                      uint32_t step_flags, float *frames, StepOut &out)
+/* body i's inverse mass / inverse moment; i = 5 is the static body */
+MSOC_HD float inv_mass(const SimCfg &c, int i) { return i < 4 ? c.agent_minv : (i == 4 ? c.ball_minv : 0.0f); }
+MSOC_HD float inv_moment(const SimCfg &c, int i) { return i < 4 ? c.agent_iinv : (i == 4 ? c.ball_iinv : 0.0f); }
+
+/* One env-step (everything except the observation frames, which the caller builds from E afterwards).
+   FAST = true is the contact-free mode used by the kernel's first pass: it returns false -- leaving E
+   meaningless and every array untouched -- as soon as the broad phase finds a candidate pair or the env
+   still carries cached arbiters; such envs are then stepped in full mode (FAST = false, always returns
+   true) on a compacted set of threads.  (A runtime flag, not a template: one copy of the code.)  `load` in [0, 7] grows with
+   the expected contact work (used to sort the compacted envs).  W is only touched when !FAST. */
+MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e,
+                      uint64_t gidx, uint32_t step_flags, Work &W, StepOut &out, int &load)
 {
     /* ---- soccer_env.py:118-125: clip to [-1, 1], scale in float32 */
     float Fx[4], Fy[4], Tq[4];
@@ -702,12 +831,18 @@ MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A
     const int old_count = (int)(E.flags & FLAG_CACHE_MASK);
     int n_contacts = 0, overflow = 0;
     int new_count = 0;
-
-    Work W;
-    W.nc = 0; W.overflow = 0; W.touched = 0ull;
     const bool contact_path = (m_as | m_aa | m_ba | m_bw) != 0u || old_count != 0;
-    if (contact_path) {
-        CacheIO cio;
+    load = 0;
+    if (FAST) {
+        if (contact_path) {
+            const int cand = popc32(m_as) + popc32(m_aa) + popc32(m_ba) + popc32(m_bw);
+            load = cand > 7 ? 7 : cand;
+            return false;
+        }
+    }
+    CacheIO cio;
+    if (!FAST && contact_path) {
+        W.nc = 0; W.overflow = 0; W.touched = 0ull;
         cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
         cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
         cio.n = A.n; cio.e = e; cio.old_count = old_count;
@@ -722,53 +857,40 @@ MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A
         /* narrow phase in canonical arbiter order: agent x segment (agent-major), agent x agent,
            ball x agent, ball x wall.  Each lane walks its own candidate list. */
         Manifold m;
+#pragma unroll 1
         while (m_as) {
-#if defined(__CUDA_ARCH__)
-            const int bit = __ffs((int)m_as) - 1;
-#else
-            const int bit = __builtin_ctz(m_as);
-#endif
+            const int bit = ctz32(m_as);
             m_as &= m_as - 1;
             const int i = bit >> 3, s = bit & 7;
             const Seg g = get_segment(s);
-            const V2 ctr = mk(gx[i], gy[i]);
-            collide_segment_box(g, ctr, gcs[i], gsn[i], m);
-            if (m.count) add_contacts(W, cio, PAIR_AGENT_SEG + bit, STATIC_BODY, i, E_AGENT_SEG, g.u, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
+            collide_segment_box(g, mk(gx[i], gy[i]), gcs[i], gsn[i], m);
+            if (m.count) add_contacts(W, cio, PAIR_AGENT_SEG + bit, STATIC_BODY, i, E_AGENT_SEG, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
         }
+#pragma unroll 1
         while (m_aa) {
-#if defined(__CUDA_ARCH__)
-            const int p = __ffs((int)m_aa) - 1;
-#else
-            const int p = __builtin_ctz(m_aa);
-#endif
+            const int p = ctz32(m_aa);
             m_aa &= m_aa - 1;
             const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
             const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
             const V2 off = mk(gx[j] - gx[i], gy[j] - gy[i]);
             collide_box_box(gcs[i], gsn[i], gcs[j], gsn[j], off, m);
-            if (m.count) add_contacts(W, cio, PAIR_AGENT_AGENT + p, i, j, E_AGENT_AGENT, U_AGENT_AGENT, m, mk(0.0f, 0.0f), off);
+            if (m.count) add_contacts(W, cio, PAIR_AGENT_AGENT + p, i, j, E_AGENT_AGENT, m, mk(0.0f, 0.0f), off);
         }
+#pragma unroll 1
         while (m_ba) {
-#if defined(__CUDA_ARCH__)
-            const int i = __ffs((int)m_ba) - 1;
-#else
-            const int i = __builtin_ctz(m_ba);
-#endif
+            const int i = ctz32(m_ba);
             m_ba &= m_ba - 1;
             const V2 cb = mk(gx[4] - gx[i], gy[4] - gy[i]);
             collide_ball_box(cb, gcs[i], gsn[i], m);
-            if (m.count) add_contacts(W, cio, PAIR_BALL_AGENT + i, BALL, i, E_BALL_AGENT, U_BALL_AGENT, m, cb, mk(0.0f, 0.0f));
+            if (m.count) add_contacts(W, cio, PAIR_BALL_AGENT + i, BALL, i, E_BALL_AGENT, m, cb, mk(0.0f, 0.0f));
         }
+#pragma unroll 1
         while (m_bw) {
-#if defined(__CUDA_ARCH__)
-            const int s = __ffs((int)m_bw) - 1;
-#else
-            const int s = __builtin_ctz(m_bw);
-#endif
+            const int s = ctz32(m_bw);
             m_bw &= m_bw - 1;
             const Seg g = get_segment(s);
             collide_ball_segment(g, mk(gx[4], gy[4]), m);
-            if (m.count) add_contacts(W, cio, PAIR_BALL_WALL + s, BALL, STATIC_BODY, E_BALL_WALL, U_BALL_WALL, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
+            if (m.count) add_contacts(W, cio, PAIR_BALL_WALL + s, BALL, STATIC_BODY, E_BALL_WALL, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
         }
         n_contacts = W.nc; overflow = W.overflow;
 
@@ -776,28 +898,27 @@ MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A
             /* ---- cpArbiterPreStep with the velocities BEFORE the velocity update */
 #pragma unroll
             for (int i = 0; i < 5; i++) {
-                W.bvx[i] = E.vx[i]; W.bvy[i] = E.vy[i]; W.bw[i] = E.w[i];
-                W.bbx[i] = 0.0f; W.bby[i] = 0.0f; W.bbw[i] = 0.0f;
-                W.bmi[i] = (i < 4) ? c.agent_minv : c.ball_minv;
-                W.bii[i] = (i < 4) ? c.agent_iinv : c.ball_iinv;
+                W.B(BF_VX, i) = E.vx[i]; W.B(BF_VY, i) = E.vy[i]; W.B(BF_W, i) = E.w[i];
+                W.B(BF_BX, i) = 0.0f; W.B(BF_BY, i) = 0.0f; W.B(BF_BW, i) = 0.0f;
             }
-            W.bvx[5] = W.bvy[5] = W.bw[5] = W.bbx[5] = W.bby[5] = W.bbw[5] = W.bmi[5] = W.bii[5] = 0.0f;
+#pragma unroll 1
             for (int k = 0; k < W.nc; k++) {
-                const int a = W.meta[k] & 7u, b = (W.meta[k] >> 3) & 7u;
-                const V2 n = mk(W.nx[k], W.ny[k]), t = vperp(n);
-                const V2 r1 = mk(W.r1x[k], W.r1y[k]), r2 = mk(W.r2x[k], W.r2y[k]);
-                const float ma = W.bmi[a], ia = W.bii[a], mb = W.bmi[b], ib = W.bii[b];
+                const uint32_t meta = f2u(W.C(CF_META, k));
+                const int a = meta & 7u, b = (meta >> 3) & 7u;
+                const V2 n = mk(W.C(CF_NX, k), W.C(CF_NY, k)), t = vperp(n);
+                const V2 r1 = mk(W.C(CF_R1X, k), W.C(CF_R1Y, k)), r2 = mk(W.C(CF_R2X, k), W.C(CF_R2Y, k));
+                const float ma = inv_mass(c, a), ia = inv_moment(c, a), mb = inv_mass(c, b), ib = inv_moment(c, b);
                 const float r1n = vcross(r1, n), r2n = vcross(r2, n), r1t = vcross(r1, t), r2t = vcross(r2, t);
-                W.nMass[k] = 1.0f / (ma + ia * r1n * r1n + mb + ib * r2n * r2n);
-                W.tMass[k] = 1.0f / (ma + ia * r1t * r1t + mb + ib * r2t * r2t);
-                const float dist = W.bias[k];
-                W.bias[k] = -BIAS_COEF_OVER_DT * fminf(0.0f, dist + SLOP);
-                const V2 va = mk(W.bvx[a], W.bvy[a]) + vperp(r1) * W.bw[a];
-                const V2 vb = mk(W.bvx[b], W.bvy[b]) + vperp(r2) * W.bw[b];
-                W.bounce[k] = vdot(vb - va, n) * W.bounce[k];
+                W.C(CF_NMASS, k) = 1.0f / (ma + ia * r1n * r1n + mb + ib * r2n * r2n);
+                W.C(CF_TMASS, k) = 1.0f / (ma + ia * r1t * r1t + mb + ib * r2t * r2t);
+                const float dist = W.C(CF_BIAS, k);
+                W.C(CF_BIAS, k) = -BIAS_COEF_OVER_DT * fminf(0.0f, dist + SLOP);
+                V2 va = mk(0.0f, 0.0f), vb = mk(0.0f, 0.0f);
+                if (a < 5) va = mk(W.B(BF_VX, a), W.B(BF_VY, a)) + vperp(r1) * W.B(BF_W, a);
+                if (b < 5) vb = mk(W.B(BF_VX, b), W.B(BF_VY, b)) + vperp(r2) * W.B(BF_W, b);
+                W.C(CF_BOUNCE, k) = vdot(vb - va, n) * W.C(CF_BOUNCE, k);
             }
         }
-
     }
 
     /* ---- cpBodyUpdateVelocity (gravity 0, damping 1) + the reference's custom velocity functions
@@ -815,73 +936,89 @@ MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A
         E.vx[i] = vx; E.vy[i] = vy;
     }
 
-    if (contact_path) {
-        CacheIO cio;
-        cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
-        cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
-        cio.n = A.n; cio.e = e; cio.old_count = old_count;
+    if (!FAST && contact_path) {
         if (W.nc > 0) {
 #pragma unroll
-            for (int i = 0; i < 5; i++) { W.bvx[i] = E.vx[i]; W.bvy[i] = E.vy[i]; W.bw[i] = E.w[i]; }
+            for (int i = 0; i < 5; i++) { W.B(BF_VX, i) = E.vx[i]; W.B(BF_VY, i) = E.vy[i]; W.B(BF_W, i) = E.w[i]; }
             /* ---- cpArbiterApplyCachedImpulse (skipped for arbiters in their first step) */
+#pragma unroll 1
             for (int k = 0; k < W.nc; k++) {
-                if ((W.meta[k] >> 16) & 1u) continue;
-                const int a = W.meta[k] & 7u, b = (W.meta[k] >> 3) & 7u;
-                const V2 n = mk(W.nx[k], W.ny[k]);
-                const V2 j = vrot(n, mk(W.jn[k], W.jt[k]));
-                const V2 r1 = mk(W.r1x[k], W.r1y[k]), r2 = mk(W.r2x[k], W.r2y[k]);
-                W.bvx[a] -= j.x * W.bmi[a]; W.bvy[a] -= j.y * W.bmi[a]; W.bw[a] -= W.bii[a] * vcross(r1, j);
-                W.bvx[b] += j.x * W.bmi[b]; W.bvy[b] += j.y * W.bmi[b]; W.bw[b] += W.bii[b] * vcross(r2, j);
+                const uint32_t meta = f2u(W.C(CF_META, k));
+                if ((meta >> 16) & 1u) continue;
+                const int a = meta & 7u, b = (meta >> 3) & 7u;
+                const V2 n = mk(W.C(CF_NX, k), W.C(CF_NY, k));
+                const V2 j = vrot(n, mk(W.C(CF_JN, k), W.C(CF_JT, k)));
+                if (a < 5) {
+                    const V2 r1 = mk(W.C(CF_R1X, k), W.C(CF_R1Y, k));
+                    const float ma = inv_mass(c, a), ia = inv_moment(c, a);
+                    W.B(BF_VX, a) -= j.x * ma; W.B(BF_VY, a) -= j.y * ma; W.B(BF_W, a) -= ia * vcross(r1, j);
+                }
+                if (b < 5) {
+                    const V2 r2 = mk(W.C(CF_R2X, k), W.C(CF_R2Y, k));
+                    const float mb = inv_mass(c, b), ib = inv_moment(c, b);
+                    W.B(BF_VX, b) += j.x * mb; W.B(BF_VY, b) += j.y * mb; W.B(BF_W, b) += ib * vcross(r2, j);
+                }
             }
             /* ---- cpArbiterApplyImpulse x 10 */
 #pragma unroll 1
             for (int it = 0; it < SOLVER_ITERS; it++) {
 #pragma unroll 1
                 for (int k = 0; k < W.nc; k++) {
-                    const int a = W.meta[k] & 7u, b = (W.meta[k] >> 3) & 7u;
-                    const V2 n = mk(W.nx[k], W.ny[k]);
-                    const V2 r1 = mk(W.r1x[k], W.r1y[k]), r2 = mk(W.r2x[k], W.r2y[k]);
-                    const float ma = W.bmi[a], ia = W.bii[a], mb = W.bmi[b], ib = W.bii[b];
-                    const V2 vb1 = mk(W.bbx[a], W.bby[a]) + vperp(r1) * W.bbw[a];
-                    const V2 vb2 = mk(W.bbx[b], W.bby[b]) + vperp(r2) * W.bbw[b];
-                    const V2 v1 = mk(W.bvx[a], W.bvy[a]) + vperp(r1) * W.bw[a];
-                    const V2 v2 = mk(W.bvx[b], W.bvy[b]) + vperp(r2) * W.bw[b];
+                    const uint32_t meta = f2u(W.C(CF_META, k));
+                    const int a = meta & 7u, b = (meta >> 3) & 7u;
+                    const V2 n = mk(W.C(CF_NX, k), W.C(CF_NY, k));
+                    const V2 r1 = mk(W.C(CF_R1X, k), W.C(CF_R1Y, k)), r2 = mk(W.C(CF_R2X, k), W.C(CF_R2Y, k));
+                    const float ma = inv_mass(c, a), ia = inv_moment(c, a), mb = inv_mass(c, b), ib = inv_moment(c, b);
+                    V2 vb1 = mk(0.0f, 0.0f), v1 = mk(0.0f, 0.0f), vb2 = mk(0.0f, 0.0f), v2 = mk(0.0f, 0.0f);
+                    if (a < 5) {
+                        vb1 = mk(W.B(BF_BX, a), W.B(BF_BY, a)) + vperp(r1) * W.B(BF_BW, a);
+                        v1 = mk(W.B(BF_VX, a), W.B(BF_VY, a)) + vperp(r1) * W.B(BF_W, a);
+                    }
+                    if (b < 5) {
+                        vb2 = mk(W.B(BF_BX, b), W.B(BF_BY, b)) + vperp(r2) * W.B(BF_BW, b);
+                        v2 = mk(W.B(BF_VX, b), W.B(BF_VY, b)) + vperp(r2) * W.B(BF_W, b);
+                    }
                     const V2 vr = v2 - v1;
                     const float vbn = vdot(vb2 - vb1, n), vrn = vdot(vr, n), vrt = vdot(vr, vperp(n));
-                    const float jbn = (W.bias[k] - vbn) * W.nMass[k];
-                    const float jbnOld = W.jb[k];
+                    const float nMass = W.C(CF_NMASS, k);
+                    const float jbn = (W.C(CF_BIAS, k) - vbn) * nMass;
+                    const float jbnOld = W.C(CF_JB, k);
                     const float jbNew = fmaxf(jbnOld + jbn, 0.0f);
-                    const float jn = -(W.bounce[k] + vrn) * W.nMass[k];
-                    const float jnOld = W.jn[k];
+                    const float jn = -(W.C(CF_BOUNCE, k) + vrn) * nMass;
+                    const float jnOld = W.C(CF_JN, k);
                     const float jnNew = fmaxf(jnOld + jn, 0.0f);
-                    const float jtMax = W.u[k] * jnNew;
-                    const float jt = -vrt * W.tMass[k];
-                    const float jtOld = W.jt[k];
+                    const float jtMax = pair_friction((int)((meta >> 6) & 63u)) * jnNew;
+                    const float jt = -vrt * W.C(CF_TMASS, k);
+                    const float jtOld = W.C(CF_JT, k);
                     const float jtNew = fminf(fmaxf(jtOld + jt, -jtMax), jtMax);
-                    W.jb[k] = jbNew; W.jn[k] = jnNew; W.jt[k] = jtNew;
+                    W.C(CF_JB, k) = jbNew; W.C(CF_JN, k) = jnNew; W.C(CF_JT, k) = jtNew;
                     const V2 jB = n * (jbNew - jbnOld);
-                    W.bbx[a] -= jB.x * ma; W.bby[a] -= jB.y * ma; W.bbw[a] -= ia * vcross(r1, jB);
-                    W.bbx[b] += jB.x * mb; W.bby[b] += jB.y * mb; W.bbw[b] += ib * vcross(r2, jB);
                     const V2 j = vrot(n, mk(jnNew - jnOld, jtNew - jtOld));
-                    W.bvx[a] -= j.x * ma; W.bvy[a] -= j.y * ma; W.bw[a] -= ia * vcross(r1, j);
-                    W.bvx[b] += j.x * mb; W.bvy[b] += j.y * mb; W.bw[b] += ib * vcross(r2, j);
+                    if (a < 5) {
+                        W.B(BF_BX, a) -= jB.x * ma; W.B(BF_BY, a) -= jB.y * ma; W.B(BF_BW, a) -= ia * vcross(r1, jB);
+                        W.B(BF_VX, a) -= j.x * ma; W.B(BF_VY, a) -= j.y * ma; W.B(BF_W, a) -= ia * vcross(r1, j);
+                    }
+                    if (b < 5) {
+                        W.B(BF_BX, b) += jB.x * mb; W.B(BF_BY, b) += jB.y * mb; W.B(BF_BW, b) += ib * vcross(r2, jB);
+                        W.B(BF_VX, b) += j.x * mb; W.B(BF_VY, b) += j.y * mb; W.B(BF_W, b) += ib * vcross(r2, j);
+                    }
                 }
             }
 #pragma unroll
             for (int i = 0; i < 5; i++) {
-                E.vx[i] = W.bvx[i]; E.vy[i] = W.bvy[i]; E.w[i] = W.bw[i];
-                E.vbx[i] = W.bbx[i]; E.vby[i] = W.bby[i];
+                E.vx[i] = W.B(BF_VX, i); E.vy[i] = W.B(BF_VY, i); E.w[i] = W.B(BF_W, i);
+                E.vbx[i] = W.B(BF_BX, i); E.vby[i] = W.B(BF_BY, i);
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) E.wb[i] = W.bbw[i];
+            for (int i = 0; i < 4; i++) E.wb[i] = W.B(BF_BW, i);
         }
 
         /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
            arbiters younger than collision_persistence (3) */
         for (int k = 0; k < W.nc && new_count < MAX_CACHE; k++) {
             const int64_t o = (int64_t)new_count * A.n + e;
-            cio.new_info[o] = (W.meta[k] >> 6) & 1023u; /* pair | key<<6, age 0 */
-            cio.new_jn[o] = W.jn[k]; cio.new_jt[o] = W.jt[k];
+            cio.new_info[o] = (f2u(W.C(CF_META, k)) >> 6) & 1023u; /* pair | key<<6, age 0 */
+            cio.new_jn[o] = W.C(CF_JN, k); cio.new_jt[o] = W.C(CF_JT, k);
             new_count++;
         }
         for (int j = 0; j < old_count; j++) {
@@ -976,7 +1113,7 @@ MSOC_HD void env_step(Env &E, const float *act, const SimCfg &c, const Arrays &A
             out.fresh_episode = true;
         }
     }
-    make_frames<FSTRIDE>(E, c, frames);
+    return true;
 }
 
 } /* namespace msoc */

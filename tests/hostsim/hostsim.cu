@@ -122,7 +122,19 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         load_env(h->A, e, E);
         StepOut out;
         float frames[4 * FRAME];
-        env_step<FRAME>(E, actions + e * 12, h->cfg, h->A, h->cur, e, h->global_offset + (uint64_t)e, flags, frames, out);
+        /* same two-instantiation flow as the kernel: contact-free fast pass first, full pass if it declines */
+        int load = 0;
+        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST];
+        Work W;
+        W.body = body; W.bstride = 1; W.con = con; W.cstride = 1;
+        const uint64_t gidx = h->global_offset + (uint64_t)e;
+        if (!env_step(true, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load)) {
+            load_env(h->A, e, E);
+            env_step(false, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load);
+        }
+        float snap[SNAP_FIELDS];
+        snapshot_env(E, snap, 1);
+        for (int a = 0; a < 4; a++) make_frame_dyn(snap, 1, a, h->cfg, frames + a * FRAME);
         store_env(h->A, e, E);
         reward[2 * e] = out.reward; reward[2 * e + 1] = out.reward;
         done[e] = out.done; goal[e] = out.goal;
