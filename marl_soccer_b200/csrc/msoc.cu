@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
 
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
     Work W;
-    W.body = s_warp + lane; W.bstride = 32;
-    W.con = s_warp + BODY_FIELDS * 5 * 32 + lane; W.cstride = 32;
+    W.body = s_warp + lane;
+    W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
     int64_t tile = blockIdx.x;
     int qhead = 0; /* total popped (block-uniform) */
 #pragma unroll 1

@@ -597,10 +597,20 @@ MSOC_HD void collide_ball_segment(const Seg &g, V2 c, Manifold &m)
    first CON_FAST contacts of an env are kept there and the rare further ones in the per-thread overflow
    array (local memory).  In tests/hostsim both are plain arrays with stride 1. */
 constexpr int CON_FAST = 4;    /* contacts per env held in shared memory */
-constexpr int CON_FIELDS = 14; /* r1x r1y r2x r2y nx ny nMass tMass bounce bias jn jt jb meta */
+constexpr int CON_FIELDS = 14;
 constexpr int BODY_FIELDS = 6; /* vx vy w bias_x bias_y bias_w, for the 5 dynamic bodies */
-enum { CF_R1X, CF_R1Y, CF_R2X, CF_R2Y, CF_NX, CF_NY, CF_NMASS, CF_TMASS, CF_BOUNCE, CF_BIAS, CF_JN, CF_JT, CF_JB, CF_META };
+/* contact record: normal, lever arms as scalars (rn = r x n, rt = r x perp(n)), effective masses,
+   bounce (restitution e until the pre-step), bias (separation until the pre-step), accumulated
+   impulses, meta = a | b<<3 | pair<<6 | key<<12 | first<<16 */
+enum { CF_NX, CF_NY, CF_RN1, CF_RT1, CF_RN2, CF_RT2, CF_NMASS, CF_TMASS, CF_BOUNCE, CF_BIAS, CF_JN, CF_JT, CF_JB, CF_META };
 enum { BF_VX, BF_VY, BF_W, BF_BX, BF_BY, BF_BW };
+#if defined(__CUDA_ARCH__)
+constexpr int SCR = 32; /* stride between consecutive scratch elements of one lane (shared memory, lane-interleaved) */
+#else
+constexpr int SCR = 1;
+#endif
+constexpr int CON_FS = CON_FAST * SCR; /* distance between two fields of a shared-memory contact */
+constexpr int BODY_FS = 5 * SCR;       /* distance between two fields of a body */
 
 MSOC_HD uint32_t f2u(float f)
 {
@@ -620,14 +630,18 @@ MSOC_HD float u2f(uint32_t u)
 }
 
 struct Work {
-    float *body; int bstride;
-    float *con; int cstride;
-    float ovf[CON_FIELDS][MAXC - CON_FAST];
+    float *body; /* field f of body i: body[f*BODY_FS + i*SCR] */
+    float *con;  /* field f of contact k < CON_FAST: con[f*CON_FS + k*SCR] */
+    float ovf[MAXC - CON_FAST][CON_FIELDS]; /* contacts CON_FAST.. (rare), field stride 1 */
     int nc, overflow;
     uint64_t touched;
-    MSOC_HD float &B(int f, int i) { return body[(f * 5 + i) * bstride]; }
-    MSOC_HD float &C(int f, int k) { return k < CON_FAST ? con[(f * CON_FAST + k) * cstride] : ovf[f][k - CON_FAST]; }
 };
+/* base pointer and field stride of contact k */
+MSOC_HD float *contact_ptr(Work &W, int k, int &fs)
+{
+    if (k < CON_FAST) { fs = CON_FS; return W.con + k * SCR; }
+    fs = 1; return &W.ovf[k - CON_FAST][0];
+}
 
 struct CacheIO {
     const uint32_t *old_info; const float *old_jn, *old_jt; /* [MAX_CACHE][n] */
@@ -667,17 +681,110 @@ MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, f
         const int k = W.nc++;
         const V2 p1 = (i == 0) ? m.p1[0] : m.p1[1], p2 = (i == 0) ? m.p2[0] : m.p2[1];
         const int key = (i == 0) ? m.key[0] : m.key[1];
-        W.C(CF_R1X, k) = p1.x - r1_off.x; W.C(CF_R1Y, k) = p1.y - r1_off.y;
-        W.C(CF_R2X, k) = p2.x - r2_off.x; W.C(CF_R2Y, k) = p2.y - r2_off.y;
-        W.C(CF_NX, k) = m.n.x; W.C(CF_NY, k) = m.n.y;
-        W.C(CF_JN, k) = (i == 0) ? cjn[0] : cjn[1];
-        W.C(CF_JT, k) = (i == 0) ? cjt[0] : cjt[1];
-        W.C(CF_JB, k) = 0.0f;
-        W.C(CF_BOUNCE, k) = e; /* restitution until the pre-step turns it into the bounce velocity */
+        const V2 r1 = p1 - r1_off, r2 = p2 - r2_off, t = vperp(m.n);
+        int fs; float *cp = contact_ptr(W, k, fs);
+        cp[CF_NX * fs] = m.n.x; cp[CF_NY * fs] = m.n.y;
+        cp[CF_RN1 * fs] = vcross(r1, m.n); cp[CF_RT1 * fs] = vcross(r1, t);
+        cp[CF_RN2 * fs] = vcross(r2, m.n); cp[CF_RT2 * fs] = vcross(r2, t);
+        cp[CF_JN * fs] = (i == 0) ? cjn[0] : cjn[1];
+        cp[CF_JT * fs] = (i == 0) ? cjt[0] : cjt[1];
+        cp[CF_JB * fs] = 0.0f;
+        cp[CF_BOUNCE * fs] = e; /* restitution until the pre-step turns it into the bounce velocity */
         /* signed separation along n from the contact points themselves (translation invariant):
            cpArbiterPreStep dist = ((r2 - r1) + (pb - pa)) . n */
-        W.C(CF_BIAS, k) = vdot(p2 - p1, m.n);
-        W.C(CF_META, k) = u2f((uint32_t)a | ((uint32_t)b << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16));
+        cp[CF_BIAS * fs] = vdot(p2 - p1, m.n);
+        cp[CF_META * fs] = u2f((uint32_t)a | ((uint32_t)b << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16));
+    }
+}
+
+/* body i's inverse mass / inverse moment; i = 5 is the static body */
+MSOC_HD float inv_mass(const SimCfg &c, int i) { return i < 4 ? c.agent_minv : (i == 4 ? c.ball_minv : 0.0f); }
+MSOC_HD float inv_moment(const SimCfg &c, int i) { return i < 4 ? c.agent_iinv : (i == 4 ? c.ball_iinv : 0.0f); }
+
+/* cpArbiterPreStep for one contact (FS = field stride of the record): effective masses, bias velocity,
+   bounce = e * (relative normal velocity BEFORE the velocity update).  With rn = r x n:
+   (v + w perp(r)) . n = v.n + w rn. */
+template <int FS>
+MSOC_HD void prestep_contact(float *cp, const float *body, const SimCfg &c)
+{
+    const uint32_t meta = f2u(cp[CF_META * FS]);
+    const int a = meta & 7u, b = (meta >> 3) & 7u;
+    const float nx = cp[CF_NX * FS], ny = cp[CF_NY * FS];
+    const float rn1 = cp[CF_RN1 * FS], rt1 = cp[CF_RT1 * FS], rn2 = cp[CF_RN2 * FS], rt2 = cp[CF_RT2 * FS];
+    const float ma = inv_mass(c, a), ia = inv_moment(c, a), mb = inv_mass(c, b), ib = inv_moment(c, b);
+    cp[CF_NMASS * FS] = 1.0f / (ma + ia * rn1 * rn1 + mb + ib * rn2 * rn2);
+    cp[CF_TMASS * FS] = 1.0f / (ma + ia * rt1 * rt1 + mb + ib * rt2 * rt2);
+    cp[CF_BIAS * FS] = -BIAS_COEF_OVER_DT * fminf(0.0f, cp[CF_BIAS * FS] + SLOP);
+    float vn = 0.0f;
+    if (a < 5) { const float *pa = body + a * SCR; vn -= pa[BF_VX * BODY_FS] * nx + pa[BF_VY * BODY_FS] * ny + pa[BF_W * BODY_FS] * rn1; }
+    if (b < 5) { const float *pb = body + b * SCR; vn += pb[BF_VX * BODY_FS] * nx + pb[BF_VY * BODY_FS] * ny + pb[BF_W * BODY_FS] * rn2; }
+    cp[CF_BOUNCE * FS] = vn * cp[CF_BOUNCE * FS];
+}
+
+/* cpArbiterApplyCachedImpulse for one contact (skipped for arbiters in their first step) */
+template <int FS>
+MSOC_HD void warmstart_contact(const float *cp, float *body, const SimCfg &c)
+{
+    const uint32_t meta = f2u(cp[CF_META * FS]);
+    if ((meta >> 16) & 1u) return;
+    const int a = meta & 7u, b = (meta >> 3) & 7u;
+    const float nx = cp[CF_NX * FS], ny = cp[CF_NY * FS], jn = cp[CF_JN * FS], jt = cp[CF_JT * FS];
+    const float jx = nx * jn - ny * jt, jy = ny * jn + nx * jt; /* n jn + perp(n) jt */
+    if (a < 5) {
+        float *pa = body + a * SCR;
+        const float ma = inv_mass(c, a), ia = inv_moment(c, a);
+        pa[BF_VX * BODY_FS] -= jx * ma; pa[BF_VY * BODY_FS] -= jy * ma;
+        pa[BF_W * BODY_FS] -= ia * (cp[CF_RN1 * FS] * jn + cp[CF_RT1 * FS] * jt);
+    }
+    if (b < 5) {
+        float *pb = body + b * SCR;
+        const float mb = inv_mass(c, b), ib = inv_moment(c, b);
+        pb[BF_VX * BODY_FS] += jx * mb; pb[BF_VY * BODY_FS] += jy * mb;
+        pb[BF_W * BODY_FS] += ib * (cp[CF_RN2 * FS] * jn + cp[CF_RT2 * FS] * jt);
+    }
+}
+
+/* cpArbiterApplyImpulse for one contact: bias impulse on the bias velocities, then normal impulse with
+   restitution and Coulomb friction clamped by the accumulated normal impulse. */
+template <int FS>
+MSOC_HD void solve_contact(float *cp, float *body, const SimCfg &c)
+{
+    const uint32_t meta = f2u(cp[CF_META * FS]);
+    const int a = meta & 7u, b = (meta >> 3) & 7u;
+    const float nx = cp[CF_NX * FS], ny = cp[CF_NY * FS];
+    const float rn1 = cp[CF_RN1 * FS], rt1 = cp[CF_RT1 * FS], rn2 = cp[CF_RN2 * FS], rt2 = cp[CF_RT2 * FS];
+    float *pa = body + a * SCR, *pb = body + b * SCR;
+    float vrn = 0.0f, vrt = 0.0f, vbn = 0.0f;
+    if (a < 5) {
+        const float vx = pa[BF_VX * BODY_FS], vy = pa[BF_VY * BODY_FS], w = pa[BF_W * BODY_FS];
+        vrn -= vx * nx + vy * ny + w * rn1;
+        vrt -= vy * nx - vx * ny + w * rt1;
+        vbn -= pa[BF_BX * BODY_FS] * nx + pa[BF_BY * BODY_FS] * ny + pa[BF_BW * BODY_FS] * rn1;
+    }
+    if (b < 5) {
+        const float vx = pb[BF_VX * BODY_FS], vy = pb[BF_VY * BODY_FS], w = pb[BF_W * BODY_FS];
+        vrn += vx * nx + vy * ny + w * rn2;
+        vrt += vy * nx - vx * ny + w * rt2;
+        vbn += pb[BF_BX * BODY_FS] * nx + pb[BF_BY * BODY_FS] * ny + pb[BF_BW * BODY_FS] * rn2;
+    }
+    const float nMass = cp[CF_NMASS * FS];
+    const float jbOld = cp[CF_JB * FS], jnOld = cp[CF_JN * FS], jtOld = cp[CF_JT * FS];
+    const float jbNew = fmaxf(jbOld + (cp[CF_BIAS * FS] - vbn) * nMass, 0.0f);
+    const float jnNew = fmaxf(jnOld - (cp[CF_BOUNCE * FS] + vrn) * nMass, 0.0f);
+    const float jtMax = pair_friction((int)((meta >> 6) & 63u)) * jnNew;
+    const float jtNew = fminf(fmaxf(jtOld - vrt * cp[CF_TMASS * FS], -jtMax), jtMax);
+    cp[CF_JB * FS] = jbNew; cp[CF_JN * FS] = jnNew; cp[CF_JT * FS] = jtNew;
+    const float djb = jbNew - jbOld, djn = jnNew - jnOld, djt = jtNew - jtOld;
+    const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+    if (a < 5) {
+        const float ma = inv_mass(c, a), ia = inv_moment(c, a);
+        pa[BF_BX * BODY_FS] -= nx * djb * ma; pa[BF_BY * BODY_FS] -= ny * djb * ma; pa[BF_BW * BODY_FS] -= ia * rn1 * djb;
+        pa[BF_VX * BODY_FS] -= jx * ma; pa[BF_VY * BODY_FS] -= jy * ma; pa[BF_W * BODY_FS] -= ia * (rn1 * djn + rt1 * djt);
+    }
+    if (b < 5) {
+        const float mb = inv_mass(c, b), ib = inv_moment(c, b);
+        pb[BF_BX * BODY_FS] += nx * djb * mb; pb[BF_BY * BODY_FS] += ny * djb * mb; pb[BF_BW * BODY_FS] += ib * rn2 * djb;
+        pb[BF_VX * BODY_FS] += jx * mb; pb[BF_VY * BODY_FS] += jy * mb; pb[BF_W * BODY_FS] += ib * (rn2 * djn + rt2 * djt);
     }
 }
 
@@ -730,10 +837,6 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
     E.steps = 0; E.score_b = 0; E.score_r = 0; E.ep_return = 0.0f;
     E.flags = ((uint32_t)mode << FLAG_MODE_SHIFT); /* cache count 0, no bias */
 }
-
-/* body i's inverse mass / inverse moment; i = 5 is the static body */
-MSOC_HD float inv_mass(const SimCfg &c, int i) { return i < 4 ? c.agent_minv : (i == 4 ? c.ball_minv : 0.0f); }
-MSOC_HD float inv_moment(const SimCfg &c, int i) { return i < 4 ? c.agent_iinv : (i == 4 ? c.ball_iinv : 0.0f); }
 
 /* One env-step (everything except the observation frames, which the caller builds from E afterwards).
    FAST = true is the contact-free mode used by the kernel's first pass: it returns false -- leaving E
@@ -898,26 +1001,15 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
             /* ---- cpArbiterPreStep with the velocities BEFORE the velocity update */
 #pragma unroll
             for (int i = 0; i < 5; i++) {
-                W.B(BF_VX, i) = E.vx[i]; W.B(BF_VY, i) = E.vy[i]; W.B(BF_W, i) = E.w[i];
-                W.B(BF_BX, i) = 0.0f; W.B(BF_BY, i) = 0.0f; W.B(BF_BW, i) = 0.0f;
+                float *pb = W.body + i * SCR;
+                pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
+                pb[BF_BX * BODY_FS] = 0.0f; pb[BF_BY * BODY_FS] = 0.0f; pb[BF_BW * BODY_FS] = 0.0f;
             }
+            const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
 #pragma unroll 1
-            for (int k = 0; k < W.nc; k++) {
-                const uint32_t meta = f2u(W.C(CF_META, k));
-                const int a = meta & 7u, b = (meta >> 3) & 7u;
-                const V2 n = mk(W.C(CF_NX, k), W.C(CF_NY, k)), t = vperp(n);
-                const V2 r1 = mk(W.C(CF_R1X, k), W.C(CF_R1Y, k)), r2 = mk(W.C(CF_R2X, k), W.C(CF_R2Y, k));
-                const float ma = inv_mass(c, a), ia = inv_moment(c, a), mb = inv_mass(c, b), ib = inv_moment(c, b);
-                const float r1n = vcross(r1, n), r2n = vcross(r2, n), r1t = vcross(r1, t), r2t = vcross(r2, t);
-                W.C(CF_NMASS, k) = 1.0f / (ma + ia * r1n * r1n + mb + ib * r2n * r2n);
-                W.C(CF_TMASS, k) = 1.0f / (ma + ia * r1t * r1t + mb + ib * r2t * r2t);
-                const float dist = W.C(CF_BIAS, k);
-                W.C(CF_BIAS, k) = -BIAS_COEF_OVER_DT * fminf(0.0f, dist + SLOP);
-                V2 va = mk(0.0f, 0.0f), vb = mk(0.0f, 0.0f);
-                if (a < 5) va = mk(W.B(BF_VX, a), W.B(BF_VY, a)) + vperp(r1) * W.B(BF_W, a);
-                if (b < 5) vb = mk(W.B(BF_VX, b), W.B(BF_VY, b)) + vperp(r2) * W.B(BF_W, b);
-                W.C(CF_BOUNCE, k) = vdot(vb - va, n) * W.C(CF_BOUNCE, k);
-            }
+            for (int k = 0; k < nfast; k++) prestep_contact<CON_FS>(W.con + k * SCR, W.body, c);
+#pragma unroll 1
+            for (int k = CON_FAST; k < W.nc; k++) prestep_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
         }
     }
 
@@ -939,86 +1031,41 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     if (!FAST && contact_path) {
         if (W.nc > 0) {
 #pragma unroll
-            for (int i = 0; i < 5; i++) { W.B(BF_VX, i) = E.vx[i]; W.B(BF_VY, i) = E.vy[i]; W.B(BF_W, i) = E.w[i]; }
-            /* ---- cpArbiterApplyCachedImpulse (skipped for arbiters in their first step) */
-#pragma unroll 1
-            for (int k = 0; k < W.nc; k++) {
-                const uint32_t meta = f2u(W.C(CF_META, k));
-                if ((meta >> 16) & 1u) continue;
-                const int a = meta & 7u, b = (meta >> 3) & 7u;
-                const V2 n = mk(W.C(CF_NX, k), W.C(CF_NY, k));
-                const V2 j = vrot(n, mk(W.C(CF_JN, k), W.C(CF_JT, k)));
-                if (a < 5) {
-                    const V2 r1 = mk(W.C(CF_R1X, k), W.C(CF_R1Y, k));
-                    const float ma = inv_mass(c, a), ia = inv_moment(c, a);
-                    W.B(BF_VX, a) -= j.x * ma; W.B(BF_VY, a) -= j.y * ma; W.B(BF_W, a) -= ia * vcross(r1, j);
-                }
-                if (b < 5) {
-                    const V2 r2 = mk(W.C(CF_R2X, k), W.C(CF_R2Y, k));
-                    const float mb = inv_mass(c, b), ib = inv_moment(c, b);
-                    W.B(BF_VX, b) += j.x * mb; W.B(BF_VY, b) += j.y * mb; W.B(BF_W, b) += ib * vcross(r2, j);
-                }
+            for (int i = 0; i < 5; i++) {
+                float *pb = W.body + i * SCR;
+                pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
             }
-            /* ---- cpArbiterApplyImpulse x 10 */
+            const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
+            /* ---- cpArbiterApplyCachedImpulse */
+#pragma unroll 1
+            for (int k = 0; k < nfast; k++) warmstart_contact<CON_FS>(W.con + k * SCR, W.body, c);
+#pragma unroll 1
+            for (int k = CON_FAST; k < W.nc; k++) warmstart_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
+            /* ---- cpArbiterApplyImpulse x 10, contacts in arbiter order */
 #pragma unroll 1
             for (int it = 0; it < SOLVER_ITERS; it++) {
 #pragma unroll 1
-                for (int k = 0; k < W.nc; k++) {
-                    const uint32_t meta = f2u(W.C(CF_META, k));
-                    const int a = meta & 7u, b = (meta >> 3) & 7u;
-                    const V2 n = mk(W.C(CF_NX, k), W.C(CF_NY, k));
-                    const V2 r1 = mk(W.C(CF_R1X, k), W.C(CF_R1Y, k)), r2 = mk(W.C(CF_R2X, k), W.C(CF_R2Y, k));
-                    const float ma = inv_mass(c, a), ia = inv_moment(c, a), mb = inv_mass(c, b), ib = inv_moment(c, b);
-                    V2 vb1 = mk(0.0f, 0.0f), v1 = mk(0.0f, 0.0f), vb2 = mk(0.0f, 0.0f), v2 = mk(0.0f, 0.0f);
-                    if (a < 5) {
-                        vb1 = mk(W.B(BF_BX, a), W.B(BF_BY, a)) + vperp(r1) * W.B(BF_BW, a);
-                        v1 = mk(W.B(BF_VX, a), W.B(BF_VY, a)) + vperp(r1) * W.B(BF_W, a);
-                    }
-                    if (b < 5) {
-                        vb2 = mk(W.B(BF_BX, b), W.B(BF_BY, b)) + vperp(r2) * W.B(BF_BW, b);
-                        v2 = mk(W.B(BF_VX, b), W.B(BF_VY, b)) + vperp(r2) * W.B(BF_W, b);
-                    }
-                    const V2 vr = v2 - v1;
-                    const float vbn = vdot(vb2 - vb1, n), vrn = vdot(vr, n), vrt = vdot(vr, vperp(n));
-                    const float nMass = W.C(CF_NMASS, k);
-                    const float jbn = (W.C(CF_BIAS, k) - vbn) * nMass;
-                    const float jbnOld = W.C(CF_JB, k);
-                    const float jbNew = fmaxf(jbnOld + jbn, 0.0f);
-                    const float jn = -(W.C(CF_BOUNCE, k) + vrn) * nMass;
-                    const float jnOld = W.C(CF_JN, k);
-                    const float jnNew = fmaxf(jnOld + jn, 0.0f);
-                    const float jtMax = pair_friction((int)((meta >> 6) & 63u)) * jnNew;
-                    const float jt = -vrt * W.C(CF_TMASS, k);
-                    const float jtOld = W.C(CF_JT, k);
-                    const float jtNew = fminf(fmaxf(jtOld + jt, -jtMax), jtMax);
-                    W.C(CF_JB, k) = jbNew; W.C(CF_JN, k) = jnNew; W.C(CF_JT, k) = jtNew;
-                    const V2 jB = n * (jbNew - jbnOld);
-                    const V2 j = vrot(n, mk(jnNew - jnOld, jtNew - jtOld));
-                    if (a < 5) {
-                        W.B(BF_BX, a) -= jB.x * ma; W.B(BF_BY, a) -= jB.y * ma; W.B(BF_BW, a) -= ia * vcross(r1, jB);
-                        W.B(BF_VX, a) -= j.x * ma; W.B(BF_VY, a) -= j.y * ma; W.B(BF_W, a) -= ia * vcross(r1, j);
-                    }
-                    if (b < 5) {
-                        W.B(BF_BX, b) += jB.x * mb; W.B(BF_BY, b) += jB.y * mb; W.B(BF_BW, b) += ib * vcross(r2, jB);
-                        W.B(BF_VX, b) += j.x * mb; W.B(BF_VY, b) += j.y * mb; W.B(BF_W, b) += ib * vcross(r2, j);
-                    }
-                }
+                for (int k = 0; k < nfast; k++) solve_contact<CON_FS>(W.con + k * SCR, W.body, c);
+#pragma unroll 1
+                for (int k = CON_FAST; k < W.nc; k++) solve_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
             }
 #pragma unroll
             for (int i = 0; i < 5; i++) {
-                E.vx[i] = W.B(BF_VX, i); E.vy[i] = W.B(BF_VY, i); E.w[i] = W.B(BF_W, i);
-                E.vbx[i] = W.B(BF_BX, i); E.vby[i] = W.B(BF_BY, i);
+                const float *pb = W.body + i * SCR;
+                E.vx[i] = pb[BF_VX * BODY_FS]; E.vy[i] = pb[BF_VY * BODY_FS]; E.w[i] = pb[BF_W * BODY_FS];
+                E.vbx[i] = pb[BF_BX * BODY_FS]; E.vby[i] = pb[BF_BY * BODY_FS];
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) E.wb[i] = W.B(BF_BW, i);
+            for (int i = 0; i < 4; i++) E.wb[i] = W.body[i * SCR + BF_BW * BODY_FS];
         }
 
         /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
            arbiters younger than collision_persistence (3) */
         for (int k = 0; k < W.nc && new_count < MAX_CACHE; k++) {
             const int64_t o = (int64_t)new_count * A.n + e;
-            cio.new_info[o] = (f2u(W.C(CF_META, k)) >> 6) & 1023u; /* pair | key<<6, age 0 */
-            cio.new_jn[o] = W.C(CF_JN, k); cio.new_jt[o] = W.C(CF_JT, k);
+            int fs; const float *cp = contact_ptr(W, k, fs);
+            cio.new_info[o] = (f2u(cp[CF_META * fs]) >> 6) & 1023u; /* pair | key<<6, age 0 */
+            cio.new_jn[o] = cp[CF_JN * fs]; cio.new_jt[o] = cp[CF_JT * fs];
             new_count++;
         }
         for (int j = 0; j < old_count; j++) {

@@ -126,7 +126,7 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         int load = 0;
         float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST];
         Work W;
-        W.body = body; W.bstride = 1; W.con = con; W.cstride = 1;
+        W.body = body; W.con = con;
         const uint64_t gidx = h->global_offset + (uint64_t)e;
         if (!env_step(true, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load)) {
             load_env(h->A, e, E);
