@@ -72,12 +72,13 @@ constexpr int WARPS_PER_BLOCK = 4;
 constexpr int BLOCK = WARPS_PER_BLOCK * 32; /* reset kernel */
 constexpr int STEP_BLOCK = 128;             /* step kernel: envs (= threads) per block */
 #ifndef MSOC_STEP_MIN_BLOCKS
-#define MSOC_STEP_MIN_BLOCKS 3
+#define MSOC_STEP_MIN_BLOCKS 4
 #endif
 constexpr int STEP_MIN_BLOCKS = MSOC_STEP_MIN_BLOCKS; /* resident blocks per SM the register budget is set for */
 
 /* ------------------------------------------------------------------ coalesced observation rows */
-constexpr int ENV_STRIDE = 89; /* floats of shared memory per env for the 4 new frames (odd: no bank conflicts) */
+constexpr int ENV_STRIDE = 109; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
+constexpr int RESET_STRIDE = 89; /* reset kernel: frame staging only */
 
 /* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns the env
    with block-local index `my_local` (envs need not be consecutive); `in2` / `out2` point at the block's
@@ -87,6 +88,7 @@ constexpr int ENV_STRIDE = 89; /* floats of shared memory per env for the 4 new 
    in `fresh` (reset / auto-reset, soccer_env.py:92-96) get three copies of the new frame.  Safe when
    obs_out == obs_in: within a batch of rows all loads precede all stores, and one env's rows are only
    ever touched by the warp that owns it. */
+template <int ENV_STRIDE>
 __device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, const float *s_new, uint32_t mask,
                                                uint32_t fresh, int64_t my_env, int lane)
 {
@@ -175,7 +177,7 @@ __device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &
 /* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
    lanes' solver bodies (30 fields) and first CON_FAST contacts (56 fields), field-major with stride 32
    (conflict-free); afterwards the lanes' four new observation frames (lane-major, stride ENV_STRIDE). */
-static_assert(BODY_FIELDS * 5 + CON_FIELDS * CON_FAST <= ENV_STRIDE, "solver scratch must fit the frame staging");
+static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
 constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
 
 /* The fused step: a persistent grid (a few blocks per SM) walks over tiles of STEP_BLOCK consecutive envs.
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
     Work W;
     W.body = s_warp + lane;
     W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
+    W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
     int64_t tile = blockIdx.x;
     int qhead = 0; /* total popped (block-uniform) */
 #pragma unroll 1
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         const uint32_t mask = __ballot_sync(0xffffffffu, ok);
         const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
         __syncwarp();
-        if (mask) write_obs_tile(in2, out2, s_warp, mask, fmask, my_env, lane);
+        if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
         if (have && !ok) s_queue[atomicAdd(&s_qtail, 1) % QUEUE_CAP] = (int)my_env;
         __syncthreads();
     }
@@ -275,7 +278,7 @@ struct ResetParams {
 
 __global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant__ ResetParams P)
 {
-    __shared__ float s_frames[WARPS_PER_BLOCK][32 * ENV_STRIDE];
+    __shared__ float s_frames[WARPS_PER_BLOCK][32 * RESET_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t block_base = (int64_t)blockIdx.x * BLOCK;
     const int64_t e = block_base + threadIdx.x;
@@ -290,13 +293,13 @@ __global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant
         env_full_reset(E, P.mode, seed, gidx, sc);
         P.A.spawn_count[e] = sc;
         store_env(P.A, e, E);
-        make_frames<22>(E, P.cfg, &s_frames[warp][lane * ENV_STRIDE]);
+        make_frames<22>(E, P.cfg, &s_frames[warp][lane * RESET_STRIDE]);
     }
     const uint32_t m = __ballot_sync(0xffffffffu, doit);
     __syncwarp();
     if (P.obs_out != nullptr && m != 0u) {
         float2 *o2 = reinterpret_cast<float2 *>(P.obs_out);
-        write_obs_tile(o2, o2, s_frames[warp], m, m, e, lane);
+        write_obs_tile<RESET_STRIDE>(o2, o2, s_frames[warp], m, m, e, lane);
     }
 }
 

@@ -629,9 +629,14 @@ MSOC_HD float u2f(uint32_t u)
 #endif
 }
 
+constexpr int GEOM_WORDS = 22; /* px[5] py[5] cos[4] sin[4] angle[4]: parked while the contact path runs */
+enum { GF_PX = 0, GF_PY = 5, GF_CS = 10, GF_SN = 14, GF_ANG = 18 };
+constexpr int SCRATCH_WORDS = BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS; /* per lane */
+
 struct Work {
     float *body; /* field f of body i: body[f*BODY_FS + i*SCR] */
     float *con;  /* field f of contact k < CON_FAST: con[f*CON_FS + k*SCR] */
+    float *geom; /* word g: geom[g*SCR] */
     float ovf[MAXC - CON_FAST][CON_FIELDS]; /* contacts CON_FAST.. (rare), field stride 1 */
     int nc, overflow;
     uint64_t touched;
@@ -943,78 +948,62 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
             return false;
         }
     }
-    CacheIO cio;
-    if (!FAST && contact_path) {
-        W.nc = 0; W.overflow = 0; W.touched = 0ull;
-        cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
-        cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
-        cio.n = A.n; cio.e = e; cio.old_count = old_count;
 
-        /* geometry with dynamic body index */
-        float gx[5], gy[5], gcs[4], gsn[4];
-#pragma unroll
-        for (int i = 0; i < 5; i++) { gx[i] = E.px[i]; gy[i] = E.py[i]; }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { gcs[i] = cs[i]; gsn[i] = sn[i]; }
-
-        /* narrow phase in canonical arbiter order: agent x segment (agent-major), agent x agent,
-           ball x agent, ball x wall.  Each lane walks its own candidate list. */
-        Manifold m;
-#pragma unroll 1
-        while (m_as) {
-            const int bit = ctz32(m_as);
-            m_as &= m_as - 1;
-            const int i = bit >> 3, s = bit & 7;
-            const Seg g = get_segment(s);
-            collide_segment_box(g, mk(gx[i], gy[i]), gcs[i], gsn[i], m);
-            if (m.count) add_contacts(W, cio, PAIR_AGENT_SEG + bit, STATIC_BODY, i, E_AGENT_SEG, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
-        }
-#pragma unroll 1
-        while (m_aa) {
-            const int p = ctz32(m_aa);
-            m_aa &= m_aa - 1;
-            const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
-            const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
-            const V2 off = mk(gx[j] - gx[i], gy[j] - gy[i]);
-            collide_box_box(gcs[i], gsn[i], gcs[j], gsn[j], off, m);
-            if (m.count) add_contacts(W, cio, PAIR_AGENT_AGENT + p, i, j, E_AGENT_AGENT, m, mk(0.0f, 0.0f), off);
-        }
-#pragma unroll 1
-        while (m_ba) {
-            const int i = ctz32(m_ba);
-            m_ba &= m_ba - 1;
-            const V2 cb = mk(gx[4] - gx[i], gy[4] - gy[i]);
-            collide_ball_box(cb, gcs[i], gsn[i], m);
-            if (m.count) add_contacts(W, cio, PAIR_BALL_AGENT + i, BALL, i, E_BALL_AGENT, m, cb, mk(0.0f, 0.0f));
-        }
-#pragma unroll 1
-        while (m_bw) {
-            const int s = ctz32(m_bw);
-            m_bw &= m_bw - 1;
-            const Seg g = get_segment(s);
-            collide_ball_segment(g, mk(gx[4], gy[4]), m);
-            if (m.count) add_contacts(W, cio, PAIR_BALL_WALL + s, BALL, STATIC_BODY, E_BALL_WALL, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
-        }
-        n_contacts = W.nc; overflow = W.overflow;
-
-        if (W.nc > 0) {
-            /* ---- cpArbiterPreStep with the velocities BEFORE the velocity update */
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                float *pb = W.body + i * SCR;
-                pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
-                pb[BF_BX * BODY_FS] = 0.0f; pb[BF_BY * BODY_FS] = 0.0f; pb[BF_BW * BODY_FS] = 0.0f;
+    /* ---- shaping rewards (game/game.py:324-349) from the step displacement; only positions enter, so
+       they are final here and their inputs need not stay live across the contact path */
+    float r = 0.0f;
+    {
+        const float ibx = incx[4], iby = incy[4];
+        if (c.prox_mult != 0.0f) {
+            float imp = 0.0f;
+            {
+                const float lx = incx[0] - ibx, ly = incy[0] - iby;
+                const float dp = sqrtf(d0x * d0x + d0y * d0y);
+                const float nx_ = d0x + lx, ny_ = d0y + ly;
+                const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
+                const float den = dp + dc;
+                if (den > 0.0f) imp += -(2.0f * (d0x * lx + d0y * ly) + (lx * lx + ly * ly)) / den;
             }
-            const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
-#pragma unroll 1
-            for (int k = 0; k < nfast; k++) prestep_contact<CON_FS>(W.con + k * SCR, W.body, c);
-#pragma unroll 1
-            for (int k = CON_FAST; k < W.nc; k++) prestep_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
+            {
+                const float lx = incx[1] - ibx, ly = incy[1] - iby;
+                const float dp = sqrtf(d1x * d1x + d1y * d1y);
+                const float nx_ = d1x + lx, ny_ = d1y + ly;
+                const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
+                const float den = dp + dc;
+                if (den > 0.0f) imp += -(2.0f * (d1x * lx + d1y * ly) + (lx * lx + ly * ly)) / den;
+            }
+            r += c.prox_mult * imp;
+        }
+        {
+            const float dp = sqrtf(dgx * dgx + dgy * dgy);
+            const float nx_ = dgx + ibx, ny_ = dgy + iby;
+            const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
+            const float den = dp + dc;
+            float imp = 0.0f;
+            if (den > 0.0f) imp = -(2.0f * (dgx * ibx + dgy * iby) + (ibx * ibx + iby * iby)) / den;
+            r += imp * c.move_mult;
+        }
+    }
+
+    if (!FAST && contact_path) {
+        /* park what the contact path needs with a dynamic body index (and what it does not need at
+           all until it is over) in the lane's scratch: pre-update velocities for the arbiter
+           pre-step, poses for the narrow phase */
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            float *pb = W.body + i * SCR;
+            pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
+            W.geom[(GF_PX + i) * SCR] = E.px[i]; W.geom[(GF_PY + i) * SCR] = E.py[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            W.geom[(GF_CS + i) * SCR] = cs[i]; W.geom[(GF_SN + i) * SCR] = sn[i]; W.geom[(GF_ANG + i) * SCR] = E.ang[i];
         }
     }
 
     /* ---- cpBodyUpdateVelocity (gravity 0, damping 1) + the reference's custom velocity functions
-       (game/entities.py:19-28 agent, :69-77 ball): friction multiplier, max_velocity clamp */
+       (game/entities.py:19-28 agent, :69-77 ball): friction multiplier, max_velocity clamp.
+       (Chipmunk runs the arbiter pre-step before this; it only reads the parked old velocities.) */
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         const bool ag = i < 4;
@@ -1029,13 +1018,63 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     }
 
     if (!FAST && contact_path) {
+        CacheIO cio;
+        W.nc = 0; W.overflow = 0; W.touched = 0ull;
+        cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
+        cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
+        cio.n = A.n; cio.e = e; cio.old_count = old_count;
+
+        /* ---- narrow phase in canonical arbiter order = ascending pair id: agent x segment
+           (agent-major), agent x agent, ball x agent, ball x wall.  Each lane walks its own candidates. */
+        uint64_t cand = (uint64_t)m_as | ((uint64_t)m_aa << PAIR_AGENT_AGENT) | ((uint64_t)m_ba << PAIR_BALL_AGENT) |
+                        ((uint64_t)m_bw << PAIR_BALL_WALL);
+        const float *G = W.geom;
+#pragma unroll 1
+        while (cand) {
+            const uint32_t lo = (uint32_t)cand, hi = (uint32_t)(cand >> 32);
+            const int pair = lo ? ctz32(lo) : 32 + ctz32(hi);
+            cand &= cand - 1;
+            Manifold m;
+            int a, b; float e_; V2 r1_off = mk(0.0f, 0.0f), r2_off = mk(0.0f, 0.0f);
+            if (pair < PAIR_AGENT_AGENT) {
+                const int i = pair >> 3, sg = pair & 7;
+                const Seg g = get_segment(sg);
+                collide_segment_box(g, mk(G[(GF_PX + i) * SCR], G[(GF_PY + i) * SCR]), G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
+                a = STATIC_BODY; b = i; e_ = E_AGENT_SEG;
+            } else if (pair < PAIR_BALL_AGENT) {
+                const int p = pair - PAIR_AGENT_AGENT;
+                const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
+                const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
+                const V2 off = mk(G[(GF_PX + j) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + j) * SCR] - G[(GF_PY + i) * SCR]);
+                collide_box_box(G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], G[(GF_CS + j) * SCR], G[(GF_SN + j) * SCR], off, m);
+                a = i; b = j; e_ = E_AGENT_AGENT; r2_off = off;
+            } else if (pair < PAIR_BALL_WALL) {
+                const int i = pair - PAIR_BALL_AGENT;
+                const V2 cb = mk(G[(GF_PX + 4) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + 4) * SCR] - G[(GF_PY + i) * SCR]);
+                collide_ball_box(cb, G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
+                a = BALL; b = i; e_ = E_BALL_AGENT; r1_off = cb;
+            } else {
+                const Seg g = get_segment(pair - PAIR_BALL_WALL);
+                collide_ball_segment(g, mk(G[(GF_PX + 4) * SCR], G[(GF_PY + 4) * SCR]), m);
+                a = BALL; b = STATIC_BODY; e_ = E_BALL_WALL;
+            }
+            if (m.count) add_contacts(W, cio, pair, a, b, e_, m, r1_off, r2_off);
+        }
+        n_contacts = W.nc; overflow = W.overflow;
+
         if (W.nc > 0) {
+            const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
+            /* ---- cpArbiterPreStep with the (parked) velocities from BEFORE the velocity update */
+#pragma unroll 1
+            for (int k = 0; k < nfast; k++) prestep_contact<CON_FS>(W.con + k * SCR, W.body, c);
+#pragma unroll 1
+            for (int k = CON_FAST; k < W.nc; k++) prestep_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
 #pragma unroll
             for (int i = 0; i < 5; i++) {
                 float *pb = W.body + i * SCR;
                 pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
+                pb[BF_BX * BODY_FS] = 0.0f; pb[BF_BY * BODY_FS] = 0.0f; pb[BF_BW * BODY_FS] = 0.0f;
             }
-            const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
             /* ---- cpArbiterApplyCachedImpulse */
 #pragma unroll 1
             for (int k = 0; k < nfast; k++) warmstart_contact<CON_FS>(W.con + k * SCR, W.body, c);
@@ -1079,6 +1118,11 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
             cio.new_jn[o] = cio.old_jn[oi]; cio.new_jt[o] = cio.old_jt[oi];
             new_count++;
         }
+        /* poses back from the scratch */
+#pragma unroll
+        for (int i = 0; i < 5; i++) { E.px[i] = W.geom[(GF_PX + i) * SCR]; E.py[i] = W.geom[(GF_PY + i) * SCR]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
     E.flags = (E.flags & ~FLAG_CACHE_MASK) | (uint32_t)new_count;
 
@@ -1088,43 +1132,10 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     if (bx < FIELD_L && GOAL_Y_BOT < by && by < GOAL_Y_TOP) { goal = -1; E.score_r++; }
     else if (bx > FIELD_R && GOAL_Y_BOT < by && by < GOAL_Y_TOP) { goal = +1; E.score_b++; }
 
-    /* ---- rewards (game/game.py:324-375) from the step displacement */
-    float r = 0.0f;
-    {
-        const float ibx = incx[4], iby = incy[4];
-        if (c.prox_mult != 0.0f) {
-            float imp = 0.0f;
-            {
-                const float lx = incx[0] - ibx, ly = incy[0] - iby;
-                const float dp = sqrtf(d0x * d0x + d0y * d0y);
-                const float nx_ = d0x + lx, ny_ = d0y + ly;
-                const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
-                const float den = dp + dc;
-                if (den > 0.0f) imp += -(2.0f * (d0x * lx + d0y * ly) + (lx * lx + ly * ly)) / den;
-            }
-            {
-                const float lx = incx[1] - ibx, ly = incy[1] - iby;
-                const float dp = sqrtf(d1x * d1x + d1y * d1y);
-                const float nx_ = d1x + lx, ny_ = d1y + ly;
-                const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
-                const float den = dp + dc;
-                if (den > 0.0f) imp += -(2.0f * (d1x * lx + d1y * ly) + (lx * lx + ly * ly)) / den;
-            }
-            r += c.prox_mult * imp;
-        }
-        {
-            const float dp = sqrtf(dgx * dgx + dgy * dgy);
-            const float nx_ = dgx + ibx, ny_ = dgy + iby;
-            const float dc = sqrtf(nx_ * nx_ + ny_ * ny_);
-            const float den = dp + dc;
-            float imp = 0.0f;
-            if (den > 0.0f) imp = -(2.0f * (dgx * ibx + dgy * iby) + (ibx * ibx + iby * iby)) / den;
-            r += imp * c.move_mult;
-        }
-        if (goal > 0) r += c.goal_reward;
-        if (goal < 0) r -= c.conceded_penalty;
-        r -= c.alive_penalty;
-    }
+    /* ---- goal / alive terms of the reward (game/game.py:362-373) */
+    if (goal > 0) r += c.goal_reward;
+    if (goal < 0) r -= c.conceded_penalty;
+    r -= c.alive_penalty;
 
     /* ---- soft reset on goal (game/game.py:421-422, :120-127): positions re-spawned in the current
        mode, velocities zeroed, agent angles 0/pi; ball angular velocity, biases, counters kept */

@@ -124,9 +124,9 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         float frames[4 * FRAME];
         /* same two-instantiation flow as the kernel: contact-free fast pass first, full pass if it declines */
         int load = 0;
-        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST];
+        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST], geom[GEOM_WORDS];
         Work W;
-        W.body = body; W.con = con;
+        W.body = body; W.con = con; W.geom = geom;
         const uint64_t gidx = h->global_offset + (uint64_t)e;
         if (!env_step(true, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load)) {
             load_env(h->A, e, E);
