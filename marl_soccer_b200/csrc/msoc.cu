@@ -80,45 +80,43 @@ constexpr int STEP_MIN_BLOCKS = MSOC_STEP_MIN_BLOCKS; /* resident blocks per SM 
 constexpr int ENV_STRIDE = 109; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
 constexpr int RESET_STRIDE = 89; /* reset kernel: frame staging only */
 
-/* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns the env
-   with block-local index `my_local` (envs need not be consecutive); `in2` / `out2` point at the block's
-   first env.  An env's 4 rows are 1 056 contiguous, 32-byte aligned bytes = 132 float2; row = 33 float2:
-   [frame t-2 | frame t-1 | frame t].  Frames t-2, t-1 come from obs_in shifted by one frame
-   (soccer_env.py:134-137), frame t from shared memory (lane l's 4 frames at s_new + l*ENV_STRIDE); envs
-   in `fresh` (reset / auto-reset, soccer_env.py:92-96) get three copies of the new frame.  Safe when
-   obs_out == obs_in: within a batch of rows all loads precede all stores, and one env's rows are only
-   ever touched by the warp that owns it. */
+/* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns env
+   `my_env` (envs need not be consecutive).  An env's 4 rows are 1 056 contiguous, 32-byte aligned bytes =
+   132 float2; row = 33 float2: [frame t-2 | frame t-1 | frame t].  Frames t-2, t-1 come from obs_in
+   shifted by one frame (soccer_env.py:134-137), frame t from shared memory (lane l's 4 frames at
+   s_new + l*ENV_STRIDE); envs in `fresh` (reset / auto-reset, soccer_env.py:92-96) get three copies of the
+   new frame.  Lane j moves float2 j of every row: fully contiguous 8-byte accesses (the +22-float shift is
+   only 8-byte aligned, so float2 is the widest access that keeps loads and stores both contiguous).
+   Safe when obs_out == obs_in: within a batch of rows all loads precede all stores, and one env's rows
+   are only ever touched by the warp that owns it. */
 template <int ENV_STRIDE>
 __device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, const float *s_new, uint32_t mask,
                                                uint32_t fresh, int64_t my_env, int lane)
 {
-    const int f_lane = lane / 11, j_lane = lane - f_lane * 11;
+    const bool lane_hist = lane < 22;                   /* float2 0-21 of a row: history; 22-31: frame t */
+    const int j_lane = lane < 11 ? lane : lane < 22 ? lane - 11 : lane - 22;
+    const float *s_lane = s_new + 2 * j_lane;           /* this lane's float2 of the staged frames */
     constexpr int RB = 8; /* rows per batch = 2 envs */
 #pragma unroll 1
     for (int l0 = 0; l0 < 32; l0 += 2) {
         const uint32_t m2 = (mask >> l0) & 3u;
         if (m2 == 0u) continue;
-        const int64_t base0 = __shfl_sync(0xffffffffu, my_env, l0) * 132;
-        const int64_t base1 = __shfl_sync(0xffffffffu, my_env, l0 + 1) * 132;
+        const int64_t e0 = __shfl_sync(0xffffffffu, my_env, l0), e1 = __shfl_sync(0xffffffffu, my_env, l0 + 1);
+        const float2 *pi[2] = {in2 + e0 * 132 + lane + 11, in2 + e1 * 132 + lane + 11};
+        float2 *po[2] = {out2 + e0 * 132 + lane, out2 + e1 * 132 + lane};
         float2 v[RB];
 #pragma unroll
         for (int u = 0; u < RB; u++) {
-            const int l = l0 + (u >> 2), a = u & 3;
-            if (!((m2 >> (u >> 2)) & 1u)) continue;
-            const int64_t row = ((u >> 2) ? base1 : base0) + a * 33;
-            if (f_lane == 2 || ((fresh >> l) & 1u)) {
-                const float *sp = s_new + l * ENV_STRIDE + a * 22 + 2 * j_lane;
-                v[u] = make_float2(sp[0], sp[1]);
-            } else {
-                v[u] = in2[row + lane + 11];
-            }
+            const int w = u >> 2, a = u & 3;
+            const float *sp = s_lane + (l0 + w) * ENV_STRIDE + a * 22;
+            v[u] = make_float2(sp[0], sp[1]);
+            if (((m2 >> w) & 1u) && lane_hist && !((fresh >> (l0 + w)) & 1u)) v[u] = pi[w][a * 33];
         }
         __syncwarp();
 #pragma unroll
         for (int u = 0; u < RB; u++) {
-            if (!((m2 >> (u >> 2)) & 1u)) continue;
-            const int64_t row = ((u >> 2) ? base1 : base0) + (u & 3) * 33;
-            out2[row + lane] = v[u];
+            const int w = u >> 2, a = u & 3;
+            if ((m2 >> w) & 1u) po[w][a * 33] = v[u];
         }
     }
     /* last float2 of every row (frame t, floats 20-21): lane l writes its own env's four */

@@ -117,13 +117,22 @@ MSOC_HD V2 vrot(V2 a, V2 r) { return mk(a.x * r.x - a.y * r.y, a.x * r.y + a.y *
 MSOC_HD V2 vlerp(V2 a, V2 b, float t) { return a * (1.0f - t) + b * t; }
 MSOC_HD float clamp01(float t) { return fminf(fmaxf(t, 0.0f), 1.0f); }
 
+/* sin and cos of an angle in [-pi - 1, pi + 1] (agent angles are kept wrapped): quadrant reduction with a
+   two-term pi/2 and the Cephes single-precision minimax polynomials on [-pi/4, pi/4]; ~1 ulp, ~30
+   instructions, no slow path (the library sincosf carries a Payne-Hanek branch per call site). */
 MSOC_HD void sincos_f(float a, float *s, float *c)
 {
-#if defined(__CUDA_ARCH__)
-    sincosf(a, s, c);
-#else
-    *s = sinf(a); *c = cosf(a);
-#endif
+    const float kf = rintf(a * 0.636619772367581343f);
+    const int k = (int)kf;
+    float r = fmaf(-kf, 1.57079625129699707031f, a);
+    r = fmaf(-kf, 7.54978941586159635335e-08f, r);
+    const float z = r * r;
+    const float sp = r + r * z * fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f);
+    const float cp = 1.0f + z * fmaf(z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), -0.5f);
+    const bool swap = k & 1;
+    const float ss = swap ? cp : sp, cc = swap ? sp : cp;
+    *s = (k & 2) ? -ss : ss;
+    *c = ((k + 1) & 2) ? -cc : cc;
 }
 MSOC_HD float rsqrt_f(float x)
 {
@@ -939,13 +948,37 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     const int old_count = (int)(E.flags & FLAG_CACHE_MASK);
     int n_contacts = 0, overflow = 0;
     int new_count = 0;
-    const bool contact_path = (m_as | m_aa | m_ba | m_bw) != 0u || old_count != 0;
+    const bool any_candidate = (m_as | m_aa | m_ba | m_bw) != 0u;
+#ifndef MSOC_FAST_AGING
+#define MSOC_FAST_AGING 1
+#endif
+#if MSOC_FAST_AGING
+    const bool contact_path = any_candidate; /* narrow phase + solver needed */
+#else
+    const bool contact_path = any_candidate || old_count != 0;
+#endif
     load = 0;
     if (FAST) {
         if (contact_path) {
             const int cand = popc32(m_as) + popc32(m_aa) + popc32(m_ba) + popc32(m_bw);
             load = cand > 7 ? 7 : cand;
             return false;
+        }
+    }
+    if (!contact_path && old_count != 0) {
+        /* nothing can touch this step, but the env still carries arbiters of contacts that ended
+           less than collision_persistence (3) steps ago: age them (cpSpaceArbiterSetFilter) */
+        const uint32_t *oi_ = A.cache_info[cur]; const float *ojn = A.cache_jn[cur], *ojt = A.cache_jt[cur];
+        uint32_t *ni_ = A.cache_info[cur ^ 1]; float *njn = A.cache_jn[cur ^ 1], *njt = A.cache_jt[cur ^ 1];
+        for (int j = 0; j < old_count; j++) {
+            const int64_t oi = (int64_t)j * A.n + e;
+            const uint32_t info = oi_[oi];
+            const uint32_t age = (info >> 10) & 3u;
+            if (age >= 2u) continue;
+            const int64_t o = (int64_t)new_count * A.n + e;
+            ni_[o] = (info & 1023u) | ((age + 1u) << 10);
+            njn[o] = ojn[oi]; njt[o] = ojt[oi];
+            new_count++;
         }
     }
 
