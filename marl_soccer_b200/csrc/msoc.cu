@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <string>
@@ -65,6 +66,8 @@ struct msoc_handle {
     int8_t *d_goal;
     int32_t *d_score;
     double *d_stats; /* 8 doubles, msoc_stats layout */
+    int *d_tile_next; /* 2 ints: dynamic tile counters, alternating between launches */
+    int launch_parity;
     void *d_stage; size_t stage_bytes; /* get/set_state staging */
 };
 
@@ -72,12 +75,12 @@ constexpr int WARPS_PER_BLOCK = 4;
 constexpr int BLOCK = WARPS_PER_BLOCK * 32; /* reset kernel */
 constexpr int STEP_BLOCK = 128;             /* step kernel: envs (= threads) per block */
 #ifndef MSOC_STEP_MIN_BLOCKS
-#define MSOC_STEP_MIN_BLOCKS 4
+#define MSOC_STEP_MIN_BLOCKS 3
 #endif
 constexpr int STEP_MIN_BLOCKS = MSOC_STEP_MIN_BLOCKS; /* resident blocks per SM the register budget is set for */
 
 /* ------------------------------------------------------------------ coalesced observation rows */
-constexpr int ENV_STRIDE = 109; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
+constexpr int ENV_STRIDE = 133; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
 constexpr int RESET_STRIDE = 89; /* reset kernel: frame staging only */
 
 /* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns env
@@ -96,27 +99,35 @@ __device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, 
     const bool lane_hist = lane < 22;                   /* float2 0-21 of a row: history; 22-31: frame t */
     const int j_lane = lane < 11 ? lane : lane < 22 ? lane - 11 : lane - 22;
     const float *s_lane = s_new + 2 * j_lane;           /* this lane's float2 of the staged frames */
-    constexpr int RB = 8; /* rows per batch = 2 envs */
+#ifndef MSOC_WRITER_ENVS
+#define MSOC_WRITER_ENVS 4
+#endif
+    constexpr int EB = MSOC_WRITER_ENVS; /* envs per batch: 4*EB row loads in flight per lane */
 #pragma unroll 1
-    for (int l0 = 0; l0 < 32; l0 += 2) {
-        const uint32_t m2 = (mask >> l0) & 3u;
-        if (m2 == 0u) continue;
-        const int64_t e0 = __shfl_sync(0xffffffffu, my_env, l0), e1 = __shfl_sync(0xffffffffu, my_env, l0 + 1);
-        const float2 *pi[2] = {in2 + e0 * 132 + lane + 11, in2 + e1 * 132 + lane + 11};
-        float2 *po[2] = {out2 + e0 * 132 + lane, out2 + e1 * 132 + lane};
-        float2 v[RB];
+    for (int l0 = 0; l0 < 32; l0 += EB) {
+        const uint32_t mb = (mask >> l0) & ((1u << EB) - 1u);
+        if (mb == 0u) continue;
+        float2 v[EB][4];
+        float2 *po[EB];
 #pragma unroll
-        for (int u = 0; u < RB; u++) {
-            const int w = u >> 2, a = u & 3;
-            const float *sp = s_lane + (l0 + w) * ENV_STRIDE + a * 22;
-            v[u] = make_float2(sp[0], sp[1]);
-            if (((m2 >> w) & 1u) && lane_hist && !((fresh >> (l0 + w)) & 1u)) v[u] = pi[w][a * 33];
+        for (int w = 0; w < EB; w++) {
+            const int64_t ew = __shfl_sync(0xffffffffu, my_env, l0 + w);
+            const float2 *pi = in2 + ew * 132 + lane + 11;
+            po[w] = out2 + ew * 132 + lane;
+            const bool ld = ((mb >> w) & 1u) && lane_hist && !((fresh >> (l0 + w)) & 1u);
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const float *sp = s_lane + (l0 + w) * ENV_STRIDE + a * 22;
+                v[w][a] = make_float2(sp[0], sp[1]);
+                if (ld) v[w][a] = pi[a * 33];
+            }
         }
         __syncwarp();
 #pragma unroll
-        for (int u = 0; u < RB; u++) {
-            const int w = u >> 2, a = u & 3;
-            if ((m2 >> w) & 1u) po[w][a * 33] = v[u];
+        for (int w = 0; w < EB; w++) {
+            if (!((mb >> w) & 1u)) continue;
+#pragma unroll
+            for (int a = 0; a < 4; a++) po[w][a * 33] = v[w][a];
         }
     }
     /* last float2 of every row (frame t, floats 20-21): lane l writes its own env's four */
@@ -141,6 +152,8 @@ struct StepParams {
     int8_t *goal;         /* (N) */
     int32_t *score;       /* (N,2) or null */
     double *stats;        /* 8 */
+    int *tile_next;       /* dynamic tile counter of this launch (starts at 0) */
+    int *tile_next_other; /* counter of the next launch: zeroed by this one */
     uint64_t global_offset;
     uint32_t flags;
     int cur;
@@ -188,18 +201,52 @@ constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(floa
    The divergent, latency-bound contact work therefore always runs on full warps, all warps of a block
    stay busy, and a single copy of the step code serves both kinds of round. */
 constexpr int QUEUE_CAP = 2 * STEP_BLOCK;
+#ifndef MSOC_PREFETCH
+#define MSOC_PREFETCH 3 /* bit 0: observation history of the current tile; bit 1: state + actions of the next tile */
+#endif
+
+/* Brings `bytes` (multiple of 16) at the 16-byte aligned global address into L2 ahead of use. */
+__device__ __forceinline__ void prefetch_l2(const void *gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+/* state arrays (16 B per env) and actions (48 B per env) of tile t, one array per lane of warp 0 */
+__device__ __forceinline__ void prefetch_tile_inputs(const StepParams &P, int64_t t, int lane)
+{
+    const int64_t first = t * STEP_BLOCK;
+    if (first >= P.A.n) return;
+    const int64_t left = P.A.n - first;
+    const uint32_t cnt = (uint32_t)(left < STEP_BLOCK ? left : STEP_BLOCK);
+    const void *ptr = nullptr; uint32_t per = 16u;
+    if (lane < 5) ptr = P.A.body[lane] + first;
+    else if (lane == 5) ptr = P.A.ang + first;
+    else if (lane == 6) ptr = P.A.angvel + first;
+    else if (lane == 7) ptr = P.A.counters + first;
+    else if (lane == 8) { ptr = P.A.ballw_ret + first; per = 8u; }
+    else if (lane == 9) { ptr = P.actions + first * 12; per = 48u; }
+    if (ptr != nullptr) {
+        const uint32_t bytes = (cnt * per) & ~15u; /* ballw_ret: 8 B per env, keep the size a multiple of 16 */
+        if (bytes) prefetch_l2(ptr, bytes);
+    }
+}
 
 __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
-    __shared__ int s_queue[QUEUE_CAP];
-    __shared__ int s_qtail; /* total pushed (monotonic) */
+    __shared__ int s_queue[2][QUEUE_CAP]; /* per work class: 0 = one agent x wall pair, 1 = everything else */
+    __shared__ int s_qtail[2];            /* total pushed (monotonic) */
+    __shared__ int s_tile;                /* next tile of this block (dynamic scheduling) */
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
     const int64_t n_tiles = (P.A.n + STEP_BLOCK - 1) / STEP_BLOCK;
     const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
     float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
-    if (tid == 0) s_qtail = 0;
+    if (tid < 2) s_qtail[tid] = 0;
+    if (tid == 0) {
+        s_tile = (int)blockIdx.x;
+        if (blockIdx.x == 0) *P.tile_next_other = 0;
+    }
     __syncthreads();
 
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
@@ -207,32 +254,48 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
     W.body = s_warp + lane;
     W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
-    int64_t tile = blockIdx.x;
-    int qhead = 0; /* total popped (block-uniform) */
+    W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
+    int qhead[2] = {0, 0}; /* total popped (block-uniform) */
+#ifdef MSOC_TIMING
+    long long cyc_tile = 0, cyc_con[2] = {0, 0}, t_start = clock64(); int n_tile = 0, n_con[2] = {0, 0}, n_con_envs[2] = {0, 0};
+    for (int i = 0; i < 8; i++) W.tm[i] = 0;
+#endif
 #pragma unroll 1
     while (true) {
-        const int qcount = s_qtail - qhead; /* block-uniform: nobody pushes between the two barriers around this read */
+        /* block-uniform: nobody pushes between the two barriers around this read */
+        const int qc0 = s_qtail[0] - qhead[0], qc1 = s_qtail[1] - qhead[1];
+        const int64_t tile = s_tile;
         __syncthreads();
         const bool tiles_left = tile < n_tiles;
-        const bool contact_round = qcount >= STEP_BLOCK || (!tiles_left && qcount > 0);
-        if (!contact_round && !tiles_left) break;
+        int cls = -1; /* -1: tile round */
+        if (qc0 >= STEP_BLOCK) cls = 0;
+        else if (qc1 >= STEP_BLOCK) cls = 1;
+        else if (!tiles_left) cls = qc0 > 0 ? 0 : (qc1 > 0 ? 1 : -1);
+        if (cls < 0 && !tiles_left) break;
+#ifdef MSOC_TIMING
+        const long long t0 = clock64();
+#endif
         int64_t my_env;
         bool have;
-        if (contact_round) {
-            const int take = qcount < STEP_BLOCK ? qcount : STEP_BLOCK;
+        int take = 0;
+        if (cls >= 0) {
+            const int qcount = cls ? qc1 : qc0;
+            take = qcount < STEP_BLOCK ? qcount : STEP_BLOCK;
             have = tid < take;
-            my_env = have ? (int64_t)s_queue[(qhead + tid) % QUEUE_CAP] : 0;
-            qhead += take;
+            my_env = have ? (int64_t)s_queue[cls][(qhead[cls] + tid) % QUEUE_CAP] : 0;
+            if (cls) qhead[1] += take; else qhead[0] += take;
         } else {
             my_env = tile * STEP_BLOCK + tid;
             have = my_env < P.A.n;
-            tile += gridDim.x;
+            /* tiles beyond the first wave are handed out dynamically, so blocks that draw cheap tiles or few
+               contact rounds take more of them (read by everybody after the barrier that ends this round) */
+            if (tid == 0) s_tile = (int)gridDim.x + atomicAdd(P.tile_next, 1);
         }
         bool fresh = false, ok = false;
         int load = 0;
         {
             Env E;
-            if (have) ok = step_one_env(!contact_round, P, my_env, E, W, load, fresh, T);
+            if (have) ok = step_one_env(cls < 0, P, my_env, E, W, load, fresh, T);
             __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
             if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
         }
@@ -240,9 +303,18 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
         __syncwarp();
         if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
-        if (have && !ok) s_queue[atomicAdd(&s_qtail, 1) % QUEUE_CAP] = (int)my_env;
+        if (have && !ok) s_queue[load][atomicAdd(&s_qtail[load], 1) % QUEUE_CAP] = (int)my_env;
         __syncthreads();
+#ifdef MSOC_TIMING
+        { const long long dt = clock64() - t0; if (cls >= 0) { cyc_con[cls] += dt; n_con[cls]++; n_con_envs[cls] += take; } else { cyc_tile += dt; n_tile++; } }
+#endif
     }
+#ifdef MSOC_TIMING
+    if (tid == 0 && (blockIdx.x % 97) == 0)
+        printf("blk %d: tile rounds %d avg %lld | light rounds %d envs %d avg %lld | heavy rounds %d envs %d avg %lld | total %lld\n", blockIdx.x, n_tile,
+               cyc_tile / (n_tile ? n_tile : 1), n_con[0], n_con_envs[0], cyc_con[0] / (n_con[0] ? n_con[0] : 1), n_con[1], n_con_envs[1],
+               cyc_con[1] / (n_con[1] ? n_con[1] : 1), clock64() - t_start);
+#endif
 
     /* per-rollout statistics (marl-soccer.ipynb:411-429): warp reduce, one atomic per warp and counter */
     int nd = T.done, gb = T.goals_b, gr = T.goals_r, nc = T.contacts, ov = T.overflow, na = T.envs;
@@ -427,6 +499,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     const size_t o_rew = take(n * 2 * sizeof(float)), o_done = take(n), o_goal = take(n), o_mask = take(n);
     const size_t o_score = take(n * 2 * sizeof(int32_t));
     const size_t o_stats = take(8 * sizeof(double));
+    const size_t o_tile = take(2 * sizeof(int));
     const size_t total = off;
 
     ce = cudaMalloc(&h->slab, total);
@@ -451,12 +524,17 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     h->d_done = (uint8_t *)(base + o_done); h->d_goal = (int8_t *)(base + o_goal); h->d_mask = (uint8_t *)(base + o_mask);
     h->d_score = (int32_t *)(base + o_score);
     h->d_stats = (double *)(base + o_stats);
+    h->d_tile_next = (int *)(base + o_tile);
 
     ce = cudaFuncSetAttribute(msoc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)STEP_SMEM_BYTES);
     if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_kernel, STEP_BLOCK, STEP_SMEM_BYTES);
+    if (const char *ov = getenv("MSOC_BLOCKS_PER_SM")) { /* tuning experiments only */
+        const int v = atoi(ov);
+        if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v;
+    }
     if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) {
         cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
     }
@@ -506,6 +584,8 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_in = d_obs_in; P.obs_out = d_obs_out;
     P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
     P.global_offset = h->global_offset; P.flags = flags; P.cur = h->cur;
+    P.tile_next = h->d_tile_next + h->launch_parity; P.tile_next_other = h->d_tile_next + (h->launch_parity ^ 1);
+    h->launch_parity ^= 1;
     const int64_t n_tiles = (h->n + STEP_BLOCK - 1) / STEP_BLOCK;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);

@@ -526,9 +526,24 @@ MSOC_HD void collide_segment_box(const Seg &g, V2 c, float cs, float sn, Manifol
     Box box; make_box(cs, sn, mk(0.0f, 0.0f), box);
     const V2 sv[2] = {g.a - c, g.b - c};
     const V2 sn2[2] = {g.n, vneg(g.n)};
-    const V2 bn[4] = {box.nrm[1], box.nrm[2], box.nrm[3], box.nrm[0]};
     V2 n; float d;
-    closest_convex<2, 4>(sv, sn2, g.il2, box.v, bn, 1.0f / 900.0f, n, d);
+    if (fminf(vdot(sv[0], sv[0]), vdot(sv[1], sv[1])) > 45.0f * 45.0f) {
+        /* Both segment ends are more than 45 px from the box centre while the bounding boxes overlap, so
+           the whole box projects onto the segment's interior with >= 38 px to spare at either end.  Then
+           neither an end point nor a box face can be the closest feature / the minimum-penetration axis
+           (a face tilted by eps against the wall loses by >= 8 |eps| px): the answer is one of the
+           segment's two faces, exactly as the general routine finds it, without its 16 point-edge tests. */
+        float s0 = INFINITY, s1 = INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            s0 = fminf(s0, vdot(box.v[j] - sv[0], g.n));
+            s1 = fminf(s1, -vdot(box.v[j] - sv[1], g.n));
+        }
+        if (s1 > s0) { n = vneg(g.n); d = s1; } else { n = g.n; d = s0; }
+    } else {
+        const V2 bn[4] = {box.nrm[1], box.nrm[2], box.nrm[3], box.nrm[0]};
+        closest_convex<2, 4>(sv, sn2, g.il2, box.v, bn, 1.0f / 900.0f, n, d);
+    }
     m.count = 0;
     if (d - g.r <= 0.0f) {
         Edge e1; e1.r = g.r;
@@ -640,16 +655,31 @@ MSOC_HD float u2f(uint32_t u)
 
 constexpr int GEOM_WORDS = 22; /* px[5] py[5] cos[4] sin[4] angle[4]: parked while the contact path runs */
 enum { GF_PX = 0, GF_PY = 5, GF_CS = 10, GF_SN = 14, GF_ANG = 18 };
-constexpr int SCRATCH_WORDS = BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS; /* per lane */
+constexpr int OLD_FAST = 8; /* cached arbiter entries (info, jn, jt) preloaded into the scratch; the rest stay in global */
+constexpr int SCRATCH_WORDS = BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS + 3 * OLD_FAST; /* per lane */
 
 struct Work {
     float *body; /* field f of body i: body[f*BODY_FS + i*SCR] */
     float *con;  /* field f of contact k < CON_FAST: con[f*CON_FS + k*SCR] */
     float *geom; /* word g: geom[g*SCR] */
+    float *old;  /* preloaded cache entry j < OLD_FAST: info old[j*SCR] (bits), jn old[(OLD_FAST+j)*SCR], jt old[(2*OLD_FAST+j)*SCR] */
     float ovf[MAXC - CON_FAST][CON_FIELDS]; /* contacts CON_FAST.. (rare), field stride 1 */
     int nc, overflow;
     uint64_t touched;
+#ifdef MSOC_TIMING
+    long long tm[8];
+#endif
 };
+#ifdef MSOC_TIMING
+#if defined(__CUDA_ARCH__)
+#define MSOC_CLOCK() clock64()
+#else
+#define MSOC_CLOCK() 0ll
+#endif
+#define MSOC_TICK(W, i, t) do { const long long _n = MSOC_CLOCK(); (W).tm[i] += _n - (t); (t) = _n; } while (0)
+#else
+#define MSOC_TICK(W, i, t) do { } while (0)
+#endif
 /* base pointer and field stride of contact k */
 MSOC_HD float *contact_ptr(Work &W, int k, int &fs)
 {
@@ -664,6 +694,21 @@ struct CacheIO {
     int old_count;
 };
 
+/* old (previous step) arbiter cache entry j: the first OLD_FAST come from the scratch (preloaded with one
+   batch of independent loads), the rare further ones from global memory */
+MSOC_HD uint32_t old_info_at(const Work &W, const CacheIO &cio, int j)
+{
+    return j < OLD_FAST ? f2u(W.old[j * SCR]) : cio.old_info[(int64_t)j * cio.n + cio.e];
+}
+MSOC_HD float old_jn_at(const Work &W, const CacheIO &cio, int j)
+{
+    return j < OLD_FAST ? W.old[(OLD_FAST + j) * SCR] : cio.old_jn[(int64_t)j * cio.n + cio.e];
+}
+MSOC_HD float old_jt_at(const Work &W, const CacheIO &cio, int j)
+{
+    return j < OLD_FAST ? W.old[(2 * OLD_FAST + j) * SCR] : cio.old_jt[(int64_t)j * cio.n + cio.e];
+}
+
 /* friction product of a pair id (cpArbiterUpdate u = ua*ub) */
 MSOC_HD float pair_friction(int pair)
 {
@@ -675,18 +720,18 @@ MSOC_HD float pair_friction(int pair)
 
 /* cpSpaceCollideShapes + cpArbiterUpdate for one touching pair: append the manifold's contacts,
    carry jnAcc/jtAcc of equal-key contacts from the cache, decide first-contact state. */
-MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, const Manifold &m,
+MSOC_HD_NOINLINE void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, const Manifold &m,
                           V2 r1_off, V2 r2_off)
 {
     W.touched |= (1ull << pair);
     bool first = true;
     float cjn[2] = {0.0f, 0.0f}, cjt[2] = {0.0f, 0.0f};
     for (int j = 0; j < cio.old_count; j++) {
-        const uint32_t info = cio.old_info[(int64_t)j * cio.n + cio.e];
+        const uint32_t info = old_info_at(W, cio, j);
         if ((int)(info & 63u) != pair) continue;
         if (((info >> 10) & 3u) == 0u) first = false;
         const int key = (int)((info >> 6) & 15u);
-        const float ojn = cio.old_jn[(int64_t)j * cio.n + cio.e], ojt = cio.old_jt[(int64_t)j * cio.n + cio.e];
+        const float ojn = old_jn_at(W, cio, j), ojt = old_jt_at(W, cio, j);
         if (m.count > 0 && key == m.key[0]) { cjn[0] = ojn; cjt[0] = ojt; }
         if (m.count > 1 && key == m.key[1]) { cjn[1] = ojn; cjt[1] = ojt; }
     }
@@ -695,11 +740,16 @@ MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, f
         const int k = W.nc++;
         const V2 p1 = (i == 0) ? m.p1[0] : m.p1[1], p2 = (i == 0) ? m.p2[0] : m.p2[1];
         const int key = (i == 0) ? m.key[0] : m.key[1];
-        const V2 r1 = p1 - r1_off, r2 = p2 - r2_off, t = vperp(m.n);
+        /* stored so that body b is dynamic: a contact (a dynamic, b static) is kept as (static, a) with the
+           normal negated and the arms exchanged -- the scalars vrn, vrt, jn, jt, dist are invariant */
+        const bool flip = (b == STATIC_BODY);
+        const V2 n_ = flip ? vneg(m.n) : m.n, t = vperp(n_);
+        const V2 r1 = flip ? p2 - r2_off : p1 - r1_off, r2 = flip ? p1 - r1_off : p2 - r2_off;
+        const int a_ = flip ? b : a, b_ = flip ? a : b;
         int fs; float *cp = contact_ptr(W, k, fs);
-        cp[CF_NX * fs] = m.n.x; cp[CF_NY * fs] = m.n.y;
-        cp[CF_RN1 * fs] = vcross(r1, m.n); cp[CF_RT1 * fs] = vcross(r1, t);
-        cp[CF_RN2 * fs] = vcross(r2, m.n); cp[CF_RT2 * fs] = vcross(r2, t);
+        cp[CF_NX * fs] = n_.x; cp[CF_NY * fs] = n_.y;
+        cp[CF_RN1 * fs] = vcross(r1, n_); cp[CF_RT1 * fs] = vcross(r1, t);
+        cp[CF_RN2 * fs] = vcross(r2, n_); cp[CF_RT2 * fs] = vcross(r2, t);
         cp[CF_JN * fs] = (i == 0) ? cjn[0] : cjn[1];
         cp[CF_JT * fs] = (i == 0) ? cjt[0] : cjt[1];
         cp[CF_JB * fs] = 0.0f;
@@ -707,7 +757,7 @@ MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, f
         /* signed separation along n from the contact points themselves (translation invariant):
            cpArbiterPreStep dist = ((r2 - r1) + (pb - pa)) . n */
         cp[CF_BIAS * fs] = vdot(p2 - p1, m.n);
-        cp[CF_META * fs] = u2f((uint32_t)a | ((uint32_t)b << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16));
+        cp[CF_META * fs] = u2f((uint32_t)a_ | ((uint32_t)b_ << 3) | ((uint32_t)pair << 6) | ((uint32_t)key << 12) | ((first ? 1u : 0u) << 16));
     }
 }
 
@@ -758,28 +808,48 @@ MSOC_HD void warmstart_contact(const float *cp, float *body, const SimCfg &c)
     }
 }
 
+/* The solver keeps the second body of the contact it is working on in registers: consecutive contacts of
+   an arbiter list usually share it (an agent's wall contacts), so the Gauss-Seidel chain does not go
+   through shared memory between them.  Contacts are stored so that body b is always dynamic. */
+struct BodyCache { int cur; float vx, vy, w, bx, by, bw; };
+MSOC_HD void bc_flush(BodyCache &bc, float *body)
+{
+    if (bc.cur >= 0) {
+        float *p = body + bc.cur * SCR;
+        p[BF_VX * BODY_FS] = bc.vx; p[BF_VY * BODY_FS] = bc.vy; p[BF_W * BODY_FS] = bc.w;
+        p[BF_BX * BODY_FS] = bc.bx; p[BF_BY * BODY_FS] = bc.by; p[BF_BW * BODY_FS] = bc.bw;
+    }
+}
+MSOC_HD void bc_acquire(BodyCache &bc, float *body, int b)
+{
+    if (bc.cur == b) return;
+    bc_flush(bc, body);
+    const float *p = body + b * SCR;
+    bc.vx = p[BF_VX * BODY_FS]; bc.vy = p[BF_VY * BODY_FS]; bc.w = p[BF_W * BODY_FS];
+    bc.bx = p[BF_BX * BODY_FS]; bc.by = p[BF_BY * BODY_FS]; bc.bw = p[BF_BW * BODY_FS];
+    bc.cur = b;
+}
+
 /* cpArbiterApplyImpulse for one contact: bias impulse on the bias velocities, then normal impulse with
    restitution and Coulomb friction clamped by the accumulated normal impulse. */
 template <int FS>
-MSOC_HD void solve_contact(float *cp, float *body, const SimCfg &c)
+MSOC_HD void solve_contact(float *cp, float *body, const SimCfg &c, BodyCache &bc)
 {
     const uint32_t meta = f2u(cp[CF_META * FS]);
     const int a = meta & 7u, b = (meta >> 3) & 7u;
+    if (a == bc.cur) { bc_flush(bc, body); bc.cur = -1; }
+    bc_acquire(bc, body, b);
     const float nx = cp[CF_NX * FS], ny = cp[CF_NY * FS];
     const float rn1 = cp[CF_RN1 * FS], rt1 = cp[CF_RT1 * FS], rn2 = cp[CF_RN2 * FS], rt2 = cp[CF_RT2 * FS];
-    float *pa = body + a * SCR, *pb = body + b * SCR;
-    float vrn = 0.0f, vrt = 0.0f, vbn = 0.0f;
+    float *pa = body + a * SCR;
+    float vrn = bc.vx * nx + bc.vy * ny + bc.w * rn2;
+    float vrt = bc.vy * nx - bc.vx * ny + bc.w * rt2;
+    float vbn = bc.bx * nx + bc.by * ny + bc.bw * rn2;
     if (a < 5) {
         const float vx = pa[BF_VX * BODY_FS], vy = pa[BF_VY * BODY_FS], w = pa[BF_W * BODY_FS];
         vrn -= vx * nx + vy * ny + w * rn1;
         vrt -= vy * nx - vx * ny + w * rt1;
         vbn -= pa[BF_BX * BODY_FS] * nx + pa[BF_BY * BODY_FS] * ny + pa[BF_BW * BODY_FS] * rn1;
-    }
-    if (b < 5) {
-        const float vx = pb[BF_VX * BODY_FS], vy = pb[BF_VY * BODY_FS], w = pb[BF_W * BODY_FS];
-        vrn += vx * nx + vy * ny + w * rn2;
-        vrt += vy * nx - vx * ny + w * rt2;
-        vbn += pb[BF_BX * BODY_FS] * nx + pb[BF_BY * BODY_FS] * ny + pb[BF_BW * BODY_FS] * rn2;
     }
     const float nMass = cp[CF_NMASS * FS];
     const float jbOld = cp[CF_JB * FS], jnOld = cp[CF_JN * FS], jtOld = cp[CF_JT * FS];
@@ -790,15 +860,15 @@ MSOC_HD void solve_contact(float *cp, float *body, const SimCfg &c)
     cp[CF_JB * FS] = jbNew; cp[CF_JN * FS] = jnNew; cp[CF_JT * FS] = jtNew;
     const float djb = jbNew - jbOld, djn = jnNew - jnOld, djt = jtNew - jtOld;
     const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+    {
+        const float mb = inv_mass(c, b), ib = inv_moment(c, b);
+        bc.bx += nx * djb * mb; bc.by += ny * djb * mb; bc.bw += ib * rn2 * djb;
+        bc.vx += jx * mb; bc.vy += jy * mb; bc.w += ib * (rn2 * djn + rt2 * djt);
+    }
     if (a < 5) {
         const float ma = inv_mass(c, a), ia = inv_moment(c, a);
         pa[BF_BX * BODY_FS] -= nx * djb * ma; pa[BF_BY * BODY_FS] -= ny * djb * ma; pa[BF_BW * BODY_FS] -= ia * rn1 * djb;
         pa[BF_VX * BODY_FS] -= jx * ma; pa[BF_VY * BODY_FS] -= jy * ma; pa[BF_W * BODY_FS] -= ia * (rn1 * djn + rt1 * djt);
-    }
-    if (b < 5) {
-        const float mb = inv_mass(c, b), ib = inv_moment(c, b);
-        pb[BF_BX * BODY_FS] += nx * djb * mb; pb[BF_BY * BODY_FS] += ny * djb * mb; pb[BF_BW * BODY_FS] += ib * rn2 * djb;
-        pb[BF_VX * BODY_FS] += jx * mb; pb[BF_VY * BODY_FS] += jy * mb; pb[BF_W * BODY_FS] += ib * (rn2 * djn + rt2 * djt);
     }
 }
 
@@ -856,11 +926,14 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
    FAST = true is the contact-free mode used by the kernel's first pass: it returns false -- leaving E
    meaningless and every array untouched -- as soon as the broad phase finds a candidate pair or the env
    still carries cached arbiters; such envs are then stepped in full mode (FAST = false, always returns
-   true) on a compacted set of threads.  (A runtime flag, not a template: one copy of the code.)  `load` in [0, 7] grows with
-   the expected contact work (used to sort the compacted envs).  W is only touched when !FAST. */
+   true) on a compacted set of threads.  (A runtime flag, not a template: one copy of the code.)  `load` is the work class of a
+   declined env (0 light, 1 heavy; see below), used to batch envs of similar contact work.  W is only touched when !FAST. */
 MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e,
                       uint64_t gidx, uint32_t step_flags, Work &W, StepOut &out, int &load)
 {
+#ifdef MSOC_TIMING
+    long long tk = MSOC_CLOCK();
+#endif
     /* ---- soccer_env.py:118-125: clip to [-1, 1], scale in float32 */
     float Fx[4], Fy[4], Tq[4];
     float cs[4], sn[4];
@@ -960,8 +1033,9 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     load = 0;
     if (FAST) {
         if (contact_path) {
-            const int cand = popc32(m_as) + popc32(m_aa) + popc32(m_ba) + popc32(m_bw);
-            load = cand > 7 ? 7 : cand;
+            /* work class for the contact queues: 0 = exactly one candidate pair and it is agent x segment
+               (the bulk: an agent touching a wall), 1 = anything else (several pairs, agent x agent, ball) */
+            load = (popc32(m_as) == 1 && (m_aa | m_ba | m_bw) == 0u) ? 0 : 1;
             return false;
         }
     }
@@ -1050,50 +1124,67 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
         E.vx[i] = vx; E.vy[i] = vy;
     }
 
+    MSOC_TICK(W, 0, tk); /* prologue .. velocity update */
     if (!FAST && contact_path) {
         CacheIO cio;
         W.nc = 0; W.overflow = 0; W.touched = 0ull;
         cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
         cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
         cio.n = A.n; cio.e = e; cio.old_count = old_count;
+        /* preload the cached arbiter entries: independent loads, one memory round trip */
+#pragma unroll
+        for (int j = 0; j < OLD_FAST; j++) {
+            if (j < old_count) {
+                const int64_t oi = (int64_t)j * A.n + e;
+                W.old[j * SCR] = u2f(cio.old_info[oi]);
+                W.old[(OLD_FAST + j) * SCR] = cio.old_jn[oi];
+                W.old[(2 * OLD_FAST + j) * SCR] = cio.old_jt[oi];
+            }
+        }
 
         /* ---- narrow phase in canonical arbiter order = ascending pair id: agent x segment
-           (agent-major), agent x agent, ball x agent, ball x wall.  Each lane walks its own candidates. */
-        uint64_t cand = (uint64_t)m_as | ((uint64_t)m_aa << PAIR_AGENT_AGENT) | ((uint64_t)m_ba << PAIR_BALL_AGENT) |
-                        ((uint64_t)m_bw << PAIR_BALL_WALL);
+           (agent-major), agent x agent, ball x agent, ball x wall.  One loop per pair type (each lane
+           walks its own candidates of that type), so a warp only pays for a collide routine as many
+           times as its busiest lane needs it. */
         const float *G = W.geom;
+        Manifold m;
 #pragma unroll 1
-        while (cand) {
-            const uint32_t lo = (uint32_t)cand, hi = (uint32_t)(cand >> 32);
-            const int pair = lo ? ctz32(lo) : 32 + ctz32(hi);
-            cand &= cand - 1;
-            Manifold m;
-            int a, b; float e_; V2 r1_off = mk(0.0f, 0.0f), r2_off = mk(0.0f, 0.0f);
-            if (pair < PAIR_AGENT_AGENT) {
-                const int i = pair >> 3, sg = pair & 7;
-                const Seg g = get_segment(sg);
-                collide_segment_box(g, mk(G[(GF_PX + i) * SCR], G[(GF_PY + i) * SCR]), G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
-                a = STATIC_BODY; b = i; e_ = E_AGENT_SEG;
-            } else if (pair < PAIR_BALL_AGENT) {
-                const int p = pair - PAIR_AGENT_AGENT;
-                const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
-                const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
-                const V2 off = mk(G[(GF_PX + j) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + j) * SCR] - G[(GF_PY + i) * SCR]);
-                collide_box_box(G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], G[(GF_CS + j) * SCR], G[(GF_SN + j) * SCR], off, m);
-                a = i; b = j; e_ = E_AGENT_AGENT; r2_off = off;
-            } else if (pair < PAIR_BALL_WALL) {
-                const int i = pair - PAIR_BALL_AGENT;
-                const V2 cb = mk(G[(GF_PX + 4) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + 4) * SCR] - G[(GF_PY + i) * SCR]);
-                collide_ball_box(cb, G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
-                a = BALL; b = i; e_ = E_BALL_AGENT; r1_off = cb;
-            } else {
-                const Seg g = get_segment(pair - PAIR_BALL_WALL);
-                collide_ball_segment(g, mk(G[(GF_PX + 4) * SCR], G[(GF_PY + 4) * SCR]), m);
-                a = BALL; b = STATIC_BODY; e_ = E_BALL_WALL;
-            }
-            if (m.count) add_contacts(W, cio, pair, a, b, e_, m, r1_off, r2_off);
+        while (m_as) {
+            const int pair = ctz32(m_as);
+            m_as &= m_as - 1;
+            const int i = pair >> 3;
+            const Seg g = get_segment(pair & 7);
+            collide_segment_box(g, mk(G[(GF_PX + i) * SCR], G[(GF_PY + i) * SCR]), G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
+            if (m.count) add_contacts(W, cio, pair, STATIC_BODY, i, E_AGENT_SEG, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
+        }
+#pragma unroll 1
+        while (m_aa) {
+            const int p = ctz32(m_aa);
+            m_aa &= m_aa - 1;
+            const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
+            const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
+            const V2 off = mk(G[(GF_PX + j) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + j) * SCR] - G[(GF_PY + i) * SCR]);
+            collide_box_box(G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], G[(GF_CS + j) * SCR], G[(GF_SN + j) * SCR], off, m);
+            if (m.count) add_contacts(W, cio, PAIR_AGENT_AGENT + p, i, j, E_AGENT_AGENT, m, mk(0.0f, 0.0f), off);
+        }
+#pragma unroll 1
+        while (m_ba) {
+            const int i = ctz32(m_ba);
+            m_ba &= m_ba - 1;
+            const V2 cb = mk(G[(GF_PX + 4) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + 4) * SCR] - G[(GF_PY + i) * SCR]);
+            collide_ball_box(cb, G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
+            if (m.count) add_contacts(W, cio, PAIR_BALL_AGENT + i, BALL, i, E_BALL_AGENT, m, cb, mk(0.0f, 0.0f));
+        }
+#pragma unroll 1
+        while (m_bw) {
+            const int sg = ctz32(m_bw);
+            m_bw &= m_bw - 1;
+            const Seg g = get_segment(sg);
+            collide_ball_segment(g, mk(G[(GF_PX + 4) * SCR], G[(GF_PY + 4) * SCR]), m);
+            if (m.count) add_contacts(W, cio, PAIR_BALL_WALL + sg, BALL, STATIC_BODY, E_BALL_WALL, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
         }
         n_contacts = W.nc; overflow = W.overflow;
+        MSOC_TICK(W, 1, tk); /* narrow phase + add_contacts */
 
         if (W.nc > 0) {
             const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
@@ -1113,14 +1204,18 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
             for (int k = 0; k < nfast; k++) warmstart_contact<CON_FS>(W.con + k * SCR, W.body, c);
 #pragma unroll 1
             for (int k = CON_FAST; k < W.nc; k++) warmstart_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
+            MSOC_TICK(W, 2, tk); /* prestep + warm start */
             /* ---- cpArbiterApplyImpulse x 10, contacts in arbiter order */
 #pragma unroll 1
+            BodyCache bc; bc.cur = -1;
+            bc.vx = bc.vy = bc.w = bc.bx = bc.by = bc.bw = 0.0f;
             for (int it = 0; it < SOLVER_ITERS; it++) {
 #pragma unroll 1
-                for (int k = 0; k < nfast; k++) solve_contact<CON_FS>(W.con + k * SCR, W.body, c);
+                for (int k = 0; k < nfast; k++) solve_contact<CON_FS>(W.con + k * SCR, W.body, c, bc);
 #pragma unroll 1
-                for (int k = CON_FAST; k < W.nc; k++) solve_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
+                for (int k = CON_FAST; k < W.nc; k++) solve_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c, bc);
             }
+            bc_flush(bc, W.body);
 #pragma unroll
             for (int i = 0; i < 5; i++) {
                 const float *pb = W.body + i * SCR;
@@ -1131,6 +1226,7 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
             for (int i = 0; i < 4; i++) E.wb[i] = W.body[i * SCR + BF_BW * BODY_FS];
         }
 
+        MSOC_TICK(W, 3, tk); /* solver */
         /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
            arbiters younger than collision_persistence (3) */
         for (int k = 0; k < W.nc && new_count < MAX_CACHE; k++) {
@@ -1141,14 +1237,13 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
             new_count++;
         }
         for (int j = 0; j < old_count; j++) {
-            const int64_t oi = (int64_t)j * A.n + e;
-            const uint32_t info = cio.old_info[oi];
+            const uint32_t info = old_info_at(W, cio, j);
             const uint32_t age = (info >> 10) & 3u;
             if (((W.touched >> (info & 63u)) & 1ull) || age >= 2u) continue;
             if (new_count >= MAX_CACHE) { overflow++; continue; }
             const int64_t o = (int64_t)new_count * A.n + e;
             cio.new_info[o] = (info & 1023u) | ((age + 1u) << 10);
-            cio.new_jn[o] = cio.old_jn[oi]; cio.new_jt[o] = cio.old_jt[oi];
+            cio.new_jn[o] = old_jn_at(W, cio, j); cio.new_jt[o] = old_jt_at(W, cio, j);
             new_count++;
         }
         /* poses back from the scratch */
@@ -1157,6 +1252,7 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
 #pragma unroll
         for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
+    MSOC_TICK(W, 4, tk); /* cache write-out */
     E.flags = (E.flags & ~FLAG_CACHE_MASK) | (uint32_t)new_count;
 
     /* ---- goal test (game/game.py:401-412), strict inequalities */

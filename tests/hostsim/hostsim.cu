@@ -26,6 +26,7 @@ struct HostSim {
     int cur;
     std::vector<std::vector<char>> mem;
     double stats[8];
+    std::vector<int32_t> last_contacts, last_load;
 };
 
 template <typename T>
@@ -117,6 +118,7 @@ void hsim_reset(HostSim *h, const uint8_t *mask, int mode, int has_seed, uint64_
 void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs_out, float *reward, uint8_t *done,
                int8_t *goal, int32_t *score, uint32_t flags)
 {
+    h->last_contacts.assign((size_t)h->n, 0); h->last_load.assign((size_t)h->n, -1);
     for (int64_t e = 0; e < h->n; e++) {
         Env E;
         load_env(h->A, e, E);
@@ -124,14 +126,16 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         float frames[4 * FRAME];
         /* same two-instantiation flow as the kernel: contact-free fast pass first, full pass if it declines */
         int load = 0;
-        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST], geom[GEOM_WORDS];
+        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST], geom[GEOM_WORDS], oldc[3 * OLD_FAST];
         Work W;
-        W.body = body; W.con = con; W.geom = geom;
+        W.body = body; W.con = con; W.geom = geom; W.old = oldc;
         const uint64_t gidx = h->global_offset + (uint64_t)e;
         if (!env_step(true, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load)) {
             load_env(h->A, e, E);
+            h->last_load[(size_t)e] = load;
             env_step(false, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load);
         }
+        h->last_contacts[(size_t)e] = out.n_contacts;
         float snap[SNAP_FIELDS];
         snapshot_env(E, snap, 1);
         for (int a = 0; a < 4; a++) make_frame_dyn(snap, 1, a, h->cfg, frames + a * FRAME);
@@ -146,6 +150,12 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         h->stats[4] += 1.0; h->stats[5] += out.n_contacts; h->stats[6] += out.overflow;
     }
     h->cur ^= 1;
+}
+
+void hsim_last(HostSim *h, int32_t *contacts, int32_t *load)
+{
+    memcpy(contacts, h->last_contacts.data(), (size_t)h->n * 4);
+    memcpy(load, h->last_load.data(), (size_t)h->n * 4);
 }
 
 void hsim_stats(HostSim *h, double *out8, int reset)
