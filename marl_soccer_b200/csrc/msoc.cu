@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
     __syncthreads();
 
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    float ovf_store[MAXC - CON_FAST][CON_FIELDS]; /* local memory, touched only by envs with more than CON_FAST contacts */
     Work W;
+    W.ovf = ovf_store;
     W.body = s_warp + lane;
     W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;

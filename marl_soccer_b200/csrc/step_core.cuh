@@ -663,7 +663,8 @@ struct Work {
     float *con;  /* field f of contact k < CON_FAST: con[f*CON_FS + k*SCR] */
     float *geom; /* word g: geom[g*SCR] */
     float *old;  /* preloaded cache entry j < OLD_FAST: info old[j*SCR] (bits), jn old[(OLD_FAST+j)*SCR], jt old[(2*OLD_FAST+j)*SCR] */
-    float ovf[MAXC - CON_FAST][CON_FIELDS]; /* contacts CON_FAST.. (rare), field stride 1 */
+    float (*ovf)[CON_FIELDS]; /* contacts CON_FAST.. (rare): caller-provided array of MAXC - CON_FAST records, field stride 1
+                                 (a pointer, so that the scalar members of this struct stay in registers) */
     int nc, overflow;
     uint64_t touched;
 #ifdef MSOC_TIMING
@@ -720,7 +721,7 @@ MSOC_HD float pair_friction(int pair)
 
 /* cpSpaceCollideShapes + cpArbiterUpdate for one touching pair: append the manifold's contacts,
    carry jnAcc/jtAcc of equal-key contacts from the cache, decide first-contact state. */
-MSOC_HD_NOINLINE void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, const Manifold &m,
+MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, float e, const Manifold &m,
                           V2 r1_off, V2 r2_off)
 {
     W.touched |= (1ull << pair);
@@ -1147,41 +1148,37 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
            walks its own candidates of that type), so a warp only pays for a collide routine as many
            times as its busiest lane needs it. */
         const float *G = W.geom;
-        Manifold m;
 #pragma unroll 1
-        while (m_as) {
-            const int pair = ctz32(m_as);
-            m_as &= m_as - 1;
-            const int i = pair >> 3;
-            const Seg g = get_segment(pair & 7);
-            collide_segment_box(g, mk(G[(GF_PX + i) * SCR], G[(GF_PY + i) * SCR]), G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
-            if (m.count) add_contacts(W, cio, pair, STATIC_BODY, i, E_AGENT_SEG, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
-        }
+        for (int phase = 0; phase < 4; phase++) { /* warp-uniform: one pair type at a time, one add_contacts site */
+            uint32_t todo = phase == 0 ? m_as : phase == 1 ? m_aa : phase == 2 ? m_ba : m_bw;
 #pragma unroll 1
-        while (m_aa) {
-            const int p = ctz32(m_aa);
-            m_aa &= m_aa - 1;
-            const int i = (p < 3) ? 0 : (p < 5) ? 1 : 2;
-            const int j = (p < 3) ? p + 1 : (p < 5) ? p - 1 : 3;
-            const V2 off = mk(G[(GF_PX + j) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + j) * SCR] - G[(GF_PY + i) * SCR]);
-            collide_box_box(G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], G[(GF_CS + j) * SCR], G[(GF_SN + j) * SCR], off, m);
-            if (m.count) add_contacts(W, cio, PAIR_AGENT_AGENT + p, i, j, E_AGENT_AGENT, m, mk(0.0f, 0.0f), off);
-        }
-#pragma unroll 1
-        while (m_ba) {
-            const int i = ctz32(m_ba);
-            m_ba &= m_ba - 1;
-            const V2 cb = mk(G[(GF_PX + 4) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + 4) * SCR] - G[(GF_PY + i) * SCR]);
-            collide_ball_box(cb, G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
-            if (m.count) add_contacts(W, cio, PAIR_BALL_AGENT + i, BALL, i, E_BALL_AGENT, m, cb, mk(0.0f, 0.0f));
-        }
-#pragma unroll 1
-        while (m_bw) {
-            const int sg = ctz32(m_bw);
-            m_bw &= m_bw - 1;
-            const Seg g = get_segment(sg);
-            collide_ball_segment(g, mk(G[(GF_PX + 4) * SCR], G[(GF_PY + 4) * SCR]), m);
-            if (m.count) add_contacts(W, cio, PAIR_BALL_WALL + sg, BALL, STATIC_BODY, E_BALL_WALL, m, mk(0.0f, 0.0f), mk(0.0f, 0.0f));
+            while (todo) {
+                const int idx = ctz32(todo);
+                todo &= todo - 1;
+                Manifold m;
+                int pair, a, b; float e_; V2 r1_off = mk(0.0f, 0.0f), r2_off = mk(0.0f, 0.0f);
+                if (phase == 0) {
+                    const int i = idx >> 3;
+                    const Seg g = get_segment(idx & 7);
+                    collide_segment_box(g, mk(G[(GF_PX + i) * SCR], G[(GF_PY + i) * SCR]), G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], m);
+                    pair = idx; a = STATIC_BODY; b = i; e_ = E_AGENT_SEG;
+                } else if (phase == 1) {
+                    const int i = (idx < 3) ? 0 : (idx < 5) ? 1 : 2;
+                    const int j = (idx < 3) ? idx + 1 : (idx < 5) ? idx - 1 : 3;
+                    const V2 off = mk(G[(GF_PX + j) * SCR] - G[(GF_PX + i) * SCR], G[(GF_PY + j) * SCR] - G[(GF_PY + i) * SCR]);
+                    collide_box_box(G[(GF_CS + i) * SCR], G[(GF_SN + i) * SCR], G[(GF_CS + j) * SCR], G[(GF_SN + j) * SCR], off, m);
+                    pair = PAIR_AGENT_AGENT + idx; a = i; b = j; e_ = E_AGENT_AGENT; r2_off = off;
+                } else if (phase == 2) {
+                    const V2 cb = mk(G[(GF_PX + 4) * SCR] - G[(GF_PX + idx) * SCR], G[(GF_PY + 4) * SCR] - G[(GF_PY + idx) * SCR]);
+                    collide_ball_box(cb, G[(GF_CS + idx) * SCR], G[(GF_SN + idx) * SCR], m);
+                    pair = PAIR_BALL_AGENT + idx; a = BALL; b = idx; e_ = E_BALL_AGENT; r1_off = cb;
+                } else {
+                    const Seg g = get_segment(idx);
+                    collide_ball_segment(g, mk(G[(GF_PX + 4) * SCR], G[(GF_PY + 4) * SCR]), m);
+                    pair = PAIR_BALL_WALL + idx; a = BALL; b = STATIC_BODY; e_ = E_BALL_WALL;
+                }
+                if (m.count) add_contacts(W, cio, pair, a, b, e_, m, r1_off, r2_off);
+            }
         }
         n_contacts = W.nc; overflow = W.overflow;
         MSOC_TICK(W, 1, tk); /* narrow phase + add_contacts */

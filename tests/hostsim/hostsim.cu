@@ -127,7 +127,9 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         /* same two-instantiation flow as the kernel: contact-free fast pass first, full pass if it declines */
         int load = 0;
         float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST], geom[GEOM_WORDS], oldc[3 * OLD_FAST];
+        float ovf_store[MAXC - CON_FAST][CON_FIELDS];
         Work W;
+        W.ovf = ovf_store;
         W.body = body; W.con = con; W.geom = geom; W.old = oldc;
         const uint64_t gidx = h->global_offset + (uint64_t)e;
         if (!env_step(true, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load)) {
