@@ -80,7 +80,7 @@ constexpr int STEP_BLOCK = 128;             /* step kernel: envs (= threads) per
 constexpr int STEP_MIN_BLOCKS = MSOC_STEP_MIN_BLOCKS; /* resident blocks per SM the register budget is set for */
 
 /* ------------------------------------------------------------------ coalesced observation rows */
-constexpr int ENV_STRIDE = 133; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
+constexpr int ENV_STRIDE = (SCRATCH_WORDS > 88 ? SCRATCH_WORDS : 88) | 1; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
 constexpr int RESET_STRIDE = 89; /* reset kernel: frame staging only */
 
 /* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns env

@@ -655,7 +655,10 @@ MSOC_HD float u2f(uint32_t u)
 
 constexpr int GEOM_WORDS = 22; /* px[5] py[5] cos[4] sin[4] angle[4]: parked while the contact path runs */
 enum { GF_PX = 0, GF_PY = 5, GF_CS = 10, GF_SN = 14, GF_ANG = 18 };
-constexpr int OLD_FAST = 8; /* cached arbiter entries (info, jn, jt) preloaded into the scratch; the rest stay in global */
+#ifndef MSOC_OLD_FAST
+#define MSOC_OLD_FAST 4
+#endif
+constexpr int OLD_FAST = MSOC_OLD_FAST; /* cached arbiter entries (info, jn, jt) preloaded into the scratch; the rest stay in global */
 constexpr int SCRATCH_WORDS = BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS + 3 * OLD_FAST; /* per lane */
 
 struct Work {
