@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         const int64_t tile = s_tile;
         __syncthreads();
         const bool tiles_left = tile < n_tiles;
-        int cls = -1; /* -1: tile round */
+        int cls = -1; /* -1: tile round, 0/1: contact round of that class, 2: final mixed flush */
         if (qc0 >= STEP_BLOCK) cls = 0;
         else if (qc1 >= STEP_BLOCK) cls = 1;
-        else if (!tiles_left) cls = qc0 > 0 ? 0 : (qc1 > 0 ? 1 : -1);
+        else if (!tiles_left) cls = (qc0 + qc1 > 0) ? 2 : -1;
         if (cls < 0 && !tiles_left) break;
 #ifdef MSOC_TIMING
         const long long t0 = clock64();
@@ -281,11 +281,16 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         bool have;
         int take = 0;
         if (cls >= 0) {
-            const int qcount = cls ? qc1 : qc0;
-            take = qcount < STEP_BLOCK ? qcount : STEP_BLOCK;
+            /* tiles are exhausted in a flush: whatever is left of both classes shares the round(s) */
+            const int take0 = cls == 1 ? 0 : (qc0 < STEP_BLOCK ? qc0 : STEP_BLOCK);
+            const int room = STEP_BLOCK - take0;
+            const int take1 = cls == 0 ? 0 : (qc1 < room ? qc1 : room);
+            take = take0 + take1;
             have = tid < take;
-            my_env = have ? (int64_t)s_queue[cls][(qhead[cls] + tid) % QUEUE_CAP] : 0;
-            if (cls) qhead[1] += take; else qhead[0] += take;
+            my_env = 0;
+            if (tid < take0) my_env = (int64_t)s_queue[0][(qhead[0] + tid) % QUEUE_CAP];
+            else if (have) my_env = (int64_t)s_queue[1][(qhead[1] + tid - take0) % QUEUE_CAP];
+            qhead[0] += take0; qhead[1] += take1;
         } else {
             my_env = tile * STEP_BLOCK + tid;
             have = my_env < P.A.n;
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         if (have && !ok) s_queue[load][atomicAdd(&s_qtail[load], 1) % QUEUE_CAP] = (int)my_env;
         __syncthreads();
 #ifdef MSOC_TIMING
-        { const long long dt = clock64() - t0; if (cls >= 0) { cyc_con[cls] += dt; n_con[cls]++; n_con_envs[cls] += take; } else { cyc_tile += dt; n_tile++; } }
+        { const long long dt = clock64() - t0; if (cls >= 0) { const int c_ = cls == 2 ? 1 : cls; cyc_con[c_] += dt; n_con[c_]++; n_con_envs[c_] += take; } else { cyc_tile += dt; n_tile++; } }
 #endif
     }
 #ifdef MSOC_TIMING
