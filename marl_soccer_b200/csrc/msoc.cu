@@ -114,7 +114,11 @@ __device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, 
             const int64_t ew = __shfl_sync(0xffffffffu, my_env, l0 + w);
             const float2 *pi = in2 + ew * 132 + lane + 11;
             po[w] = out2 + ew * 132 + lane;
+#ifdef MSOC_EXP_NOHIST /* timing experiment only: no history loads (wrong observations) */
+            const bool ld = false;
+#else
             const bool ld = ((mb >> w) & 1u) && lane_hist && !((fresh >> (l0 + w)) & 1u);
+#endif
 #pragma unroll
             for (int a = 0; a < 4; a++) {
                 const float *sp = s_lane + (l0 + w) * ENV_STRIDE + a * 22;
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
     int qhead[2] = {0, 0}; /* total popped (block-uniform) */
 #ifdef MSOC_TIMING
     long long cyc_tile = 0, cyc_con[2] = {0, 0}, t_start = clock64(); int n_tile = 0, n_con[2] = {0, 0}, n_con_envs[2] = {0, 0};
+    long long ph[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}, tmc[3][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}; /* per round kind: step, frames, writer, barrier | env_step phases */
     for (int i = 0; i < 8; i++) W.tm[i] = 0;
 #endif
 #pragma unroll 1
@@ -300,19 +305,32 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         }
         bool fresh = false, ok = false;
         int load = 0;
+#ifdef MSOC_TIMING
+        const int kind = cls < 0 ? 0 : (cls == 0 ? 1 : 2);
+        long long tmb[5]; for (int i = 0; i < 5; i++) tmb[i] = W.tm[i];
+        long long tp = clock64();
+#define PH(i) do { __syncwarp(); const long long n_ = clock64(); ph[kind][i] += n_ - tp; tp = n_; } while (0)
+#else
+#define PH(i) do { } while (0)
+#endif
         {
             Env E;
             if (have) ok = step_one_env(cls < 0, P, my_env, E, W, load, fresh, T);
             __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
+            PH(0);
             if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, ok);
         const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
         __syncwarp();
+        PH(1);
         if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
         if (have && !ok) s_queue[load][atomicAdd(&s_qtail[load], 1) % QUEUE_CAP] = (int)my_env;
+        PH(2);
         __syncthreads();
+        PH(3);
 #ifdef MSOC_TIMING
+        for (int i = 0; i < 5; i++) tmc[kind][i] += W.tm[i] - tmb[i];
         { const long long dt = clock64() - t0; if (cls >= 0) { const int c_ = cls == 2 ? 1 : cls; cyc_con[c_] += dt; n_con[c_]++; n_con_envs[c_] += take; } else { cyc_tile += dt; n_tile++; } }
 #endif
     }
@@ -321,6 +339,10 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         printf("blk %d: tile rounds %d avg %lld | light rounds %d envs %d avg %lld | heavy rounds %d envs %d avg %lld | total %lld\n", blockIdx.x, n_tile,
                cyc_tile / (n_tile ? n_tile : 1), n_con[0], n_con_envs[0], cyc_con[0] / (n_con[0] ? n_con[0] : 1), n_con[1], n_con_envs[1],
                cyc_con[1] / (n_con[1] ? n_con[1] : 1), clock64() - t_start);
+    if (lane == 0 && (blockIdx.x % 97) == 0)
+        for (int k = 0; k < 3; k++)
+            printf("  blk %d warp %d kind %d: step %lld frames %lld writer %lld barrier %lld | prologue %lld narrow %lld prestep %lld solver %lld cacheout %lld\n", blockIdx.x, warp, k,
+                   ph[k][0], ph[k][1], ph[k][2], ph[k][3], tmc[k][0], tmc[k][1], tmc[k][2], tmc[k][3], tmc[k][4]);
 #endif
 
     /* per-rollout statistics (marl-soccer.ipynb:411-429): warp reduce, one atomic per warp and counter */

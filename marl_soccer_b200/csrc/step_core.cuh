@@ -620,7 +620,10 @@ MSOC_HD void collide_ball_segment(const Seg &g, V2 c, Manifold &m)
    memory (conflict-free: element (field, index) of thread t lives at (field*K + index)*stride + t), the
    first CON_FAST contacts of an env are kept there and the rare further ones in the per-thread overflow
    array (local memory).  In tests/hostsim both are plain arrays with stride 1. */
-constexpr int CON_FAST = 4;    /* contacts per env held in shared memory */
+#ifndef MSOC_CON_FAST
+#define MSOC_CON_FAST 4
+#endif
+constexpr int CON_FAST = MSOC_CON_FAST; /* contacts per env held in shared memory */
 constexpr int CON_FIELDS = 14;
 constexpr int BODY_FIELDS = 6; /* vx vy w bias_x bias_y bias_w, for the 5 dynamic bodies */
 /* contact record: normal, lever arms as scalars (rn = r x n, rt = r x perp(n)), effective masses,
@@ -1035,7 +1038,19 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     const bool contact_path = any_candidate || old_count != 0;
 #endif
     load = 0;
-    if (FAST) {
+#ifndef MSOC_INLINE_STATIC
+#define MSOC_INLINE_STATIC 0
+#endif
+#if MSOC_INLINE_STATIC
+    /* envs whose candidate pairs are all body x static segment are solved in place (each body is an
+       independent sub-problem); only envs with a dynamic x dynamic candidate pair go to the queue */
+    const bool inline_ok = (m_aa | m_ba) == 0u && old_count <= OLD_FAST;
+    const bool run_contacts = contact_path && (!FAST || inline_ok);
+#else
+    const bool inline_ok = false;
+    const bool run_contacts = !FAST && contact_path;
+#endif
+    if (FAST && !inline_ok) {
         if (contact_path) {
             /* work class for the contact queues: 0 = exactly one candidate pair and it is agent x segment
                (the bulk: an agent touching a wall), 1 = anything else (several pairs, agent x agent, ball) */
@@ -1096,7 +1111,7 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
         }
     }
 
-    if (!FAST && contact_path) {
+    if (run_contacts) {
         /* park what the contact path needs with a dynamic body index (and what it does not need at
            all until it is over) in the lane's scratch: pre-update velocities for the arbiter
            pre-step, poses for the narrow phase */
@@ -1129,7 +1144,7 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     }
 
     MSOC_TICK(W, 0, tk); /* prologue .. velocity update */
-    if (!FAST && contact_path) {
+    if (run_contacts) {
         CacheIO cio;
         W.nc = 0; W.overflow = 0; W.touched = 0ull;
         cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];

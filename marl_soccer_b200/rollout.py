@@ -1,0 +1,152 @@
+"""Device-resident rollout half of the reference's PPO trainer (marl-soccer.ipynb:366-431) -- the immediate
+caller of the hot path (BASELINE config 5).
+
+Everything the notebook does around `envs.step` per rollout step stays on the GPU: observation normalisation
+`clip((x - mean) / (std + 1e-8), -10, 10)` (:385), the policy/value MLPs (:125-190), action sampling, uniform
+random actions for the red agents (:397-400), reward / done / value / log-prob storage (:403-409), and the
+running mean/variance update (:264-296, :431).  The simulator is `BatchedSoccerSim` (one fused CUDA kernel per
+step); nothing crosses PCIe inside the loop.  The network architecture and the normaliser arithmetic mirror
+the reference so that its checkpoints (`runs/*/ppo_pettingzoo_soccer.ppo_model`,
+`latest_normalizer_stats.npz`) load unchanged.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.distributions.normal import Normal
+
+
+def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+class Agent(nn.Module):
+    """Actor / critic MLPs 66 -> 512 -> 256 -> 128 -> 64 -> (3 | 1), tanh (marl-soccer.ipynb:125-190; same
+    parameter names, so `load_state_dict` of a reference checkpoint works)."""
+
+    def __init__(self, obs_dim: int = 66, act_dim: int = 3, rpo_alpha: float = 0.0):
+        super().__init__()
+        self.critic = nn.Sequential(
+            layer_init(nn.Linear(obs_dim, 512)), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(), nn.Linear(256, 128), nn.Tanh(),
+            layer_init(nn.Linear(128, 64)), nn.Tanh(), layer_init(nn.Linear(64, 1), std=1.0))
+        self.actor_mean = nn.Sequential(
+            layer_init(nn.Linear(obs_dim, 512)), nn.Tanh(), nn.Linear(512, 256), nn.Tanh(), nn.Linear(256, 128), nn.Tanh(),
+            layer_init(nn.Linear(128, 64)), nn.Tanh(), layer_init(nn.Linear(64, act_dim), std=0.01))
+        self.actor_logstd = nn.Parameter(torch.zeros(1, act_dim))
+        self.rpo_alpha = rpo_alpha
+
+    def get_value(self, x):
+        return self.critic(x)
+
+    def get_action_and_value(self, x, action=None):
+        mean = self.actor_mean(x)
+        std = torch.exp(self.actor_logstd.expand_as(mean))
+        probs = Normal(mean, std)
+        if action is None:
+            action = probs.sample()
+        elif self.rpo_alpha > 0.0:
+            z = torch.empty_like(mean).uniform_(-self.rpo_alpha, self.rpo_alpha)
+            probs = Normal(mean + z, std)
+        return action, probs.log_prob(action).sum(1), probs.entropy().sum(1), self.critic(x)
+
+    def get_deterministic_action(self, x):
+        return self.actor_mean(x)
+
+
+class RunningMeanStd:
+    """Welford running mean / variance over a stream of observation batches, float64 on the device
+    (marl-soccer.ipynb:264-296)."""
+
+    def __init__(self, shape, device):
+        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
+        self.var = torch.ones(shape, dtype=torch.float64, device=device)
+        self.count = 0
+
+    def update(self, x: torch.Tensor) -> None:
+        x = x.reshape(-1, self.mean.shape[-1]).to(torch.float64)
+        batch_mean, batch_var, n = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        delta = batch_mean - self.mean
+        tot = self.count + n
+        self.mean = self.mean + delta * (n / tot)
+        m2 = self.var * self.count + batch_var * n + delta.square() * (self.count * n / tot)
+        self.var = m2 / tot
+        self.count = tot
+
+    @property
+    def std(self):
+        return self.var.sqrt()
+
+    def load_npz(self, path: str) -> None:
+        z = np.load(path)
+        self.mean = torch.as_tensor(z["mean"], dtype=torch.float64, device=self.mean.device)
+        self.var = torch.as_tensor(z["var"], dtype=torch.float64, device=self.mean.device)
+
+    def normalize(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.clamp((x - self.mean.float()) / (self.std.float() + 1e-8), -10.0, 10.0)
+
+
+class RolloutBuffer:
+    """(T, N, 2, ...) storage of one rollout for the two trainable (blue) agents, on the device."""
+
+    def __init__(self, num_steps: int, num_envs: int, device, obs_dtype=torch.float32):
+        T, N = num_steps, num_envs
+        self.obs = torch.zeros((T, N, 2, 66), dtype=obs_dtype, device=device)
+        self.actions = torch.zeros((T, N, 2, 3), device=device)
+        self.logprobs = torch.zeros((T, N, 2), device=device)
+        self.rewards = torch.zeros((T, N, 2), device=device)
+        self.dones = torch.zeros((T, N, 2), device=device)
+        self.values = torch.zeros((T, N, 2), device=device)
+
+
+@torch.no_grad()
+def collect_rollout(sim, agent: Agent, normalizer: RunningMeanStd, buf: RolloutBuffer, next_obs: torch.Tensor,
+                    next_done: torch.Tensor, generator=None, update_normalizer: bool = True, policy_dtype=None):
+    """One rollout of `buf.obs.shape[0]` steps (marl-soccer.ipynb:366-431): blue = policy, red = U(-1, 1).
+    next_obs: (N, 2, 66) raw observations of the blue agents; next_done: (N, 2).  Returns the updated pair.
+    policy_dtype: optional autocast dtype for the MLPs (e.g. torch.bfloat16); the simulator is always fp32."""
+    T = buf.obs.shape[0]
+    n = sim.num_envs
+    dev = sim.device
+    full = sim.actions  # (N, 4, 3) device buffer of the handle
+    for t in range(T):
+        buf.obs[t] = next_obs
+        buf.dones[t] = next_done
+        x = normalizer.normalize(next_obs.reshape(-1, 66))
+        if policy_dtype is not None:
+            with torch.autocast(device_type="cuda", dtype=policy_dtype):
+                action, logprob, _, value = agent.get_action_and_value(x)
+            action, logprob, value = action.float(), logprob.float(), value.float()
+        else:
+            action, logprob, _, value = agent.get_action_and_value(x)
+        buf.values[t] = value.reshape(n, 2)
+        buf.actions[t] = action.reshape(n, 2, 3)
+        buf.logprobs[t] = logprob.reshape(n, 2)
+        full[:, :2] = buf.actions[t]
+        full[:, 2:].uniform_(-1.0, 1.0, generator=generator)
+        obs, reward, done, _goal = sim.step(full, auto_reset=True)
+        buf.rewards[t] = reward
+        next_obs = obs[:, :2].clone()
+        next_done = done.to(torch.float32)[:, None].expand(n, 2)
+    if update_normalizer:
+        normalizer.update(buf.obs.reshape(-1, 66))
+    return next_obs, next_done
+
+
+@torch.no_grad()
+def compute_gae(agent: Agent, normalizer: RunningMeanStd, buf: RolloutBuffer, next_obs, next_done, gamma=0.995,
+                gae_lambda=0.95):
+    """Generalised advantage estimation over the rollout (marl-soccer.ipynb:454-464)."""
+    T, n = buf.rewards.shape[0], buf.rewards.shape[1]
+    next_value = agent.get_value(normalizer.normalize(next_obs.reshape(-1, 66))).reshape(n, 2)
+    adv = torch.zeros_like(buf.rewards)
+    last = torch.zeros((n, 2), device=buf.rewards.device)
+    for t in reversed(range(T)):
+        nonterminal = 1.0 - (next_done if t == T - 1 else buf.dones[t + 1])
+        nv = next_value if t == T - 1 else buf.values[t + 1]
+        delta = buf.rewards[t] + gamma * nv * nonterminal - buf.values[t]
+        last = delta + gamma * gae_lambda * nonterminal * last
+        adv[t] = last
+    return adv, adv + buf.values
