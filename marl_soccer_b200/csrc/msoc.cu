@@ -58,7 +58,7 @@ struct msoc_handle {
     SimCfg cfg;
     Arrays A;
     int cur; /* which half of the ping-pong arbiter cache is current */
-    int sm_count, blocks_per_sm; /* persistent grid of the step kernel */
+    int sm_count, blocks_per_sm; /* persistent grid of the contact kernel */
     void *slab;
     /* internal I/O buffers of the host-buffer API */
     float *d_obs, *d_act, *d_rew;
@@ -66,12 +66,9 @@ struct msoc_handle {
     int8_t *d_goal;
     int32_t *d_score;
     double *d_stats; /* 8 doubles, msoc_stats layout */
-    /* scheduling state of the step kernel */
-    int *d_ctl;        /* 3 x CTL_WORDS counters, rotating: this launch / next launch / being zeroed */
-    int *d_list[2];    /* n ints each: contact lists read by this launch / written for the next */
-    int *d_dynq;       /* n ints: dynamic queue (all -1 between launches) */
-    uint8_t *d_hint[2]; /* n bytes each: != 0 -> env is on the list of that launch */
-    uint64_t step_seq; /* launches so far */
+    int *d_ctl;  /* 2 x CTL_WORDS counters of the step kernels, alternating between steps */
+    int *d_list; /* n ints: contact list of the step in flight */
+    int step_parity;
     void *d_stage; size_t stage_bytes; /* get/set_state staging */
 };
 
@@ -104,7 +101,7 @@ __device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, 
     const int j_lane = lane < 11 ? lane : lane < 22 ? lane - 11 : lane - 22;
     const float *s_lane = s_new + 2 * j_lane;           /* this lane's float2 of the staged frames */
 #ifndef MSOC_WRITER_ENVS
-#define MSOC_WRITER_ENVS 4
+#define MSOC_WRITER_ENVS 8
 #endif
     constexpr int EB = MSOC_WRITER_ENVS; /* envs per batch: 4*EB row loads in flight per lane */
 #pragma unroll 1
@@ -160,15 +157,9 @@ struct StepParams {
     int8_t *goal;         /* (N) */
     int32_t *score;       /* (N,2) or null */
     double *stats;        /* 8 */
-    /* scheduling state (see msoc_step_kernel) */
-    int *ctl;             /* counters of this launch, CTL_* below: its list sizes were counted by the previous launch */
-    int *ctl_next;        /* counters of the next launch: this launch counts that launch's lists */
-    int *ctl_zero;        /* counters of the launch after the next: zeroed by this one */
-    const int *list;      /* N slots: envs expected to need contact work -- light from the front, heavy from the back */
-    int *list_next;       /* the same for the next launch, appended to by this one */
-    int *dynq;            /* N slots: envs found to need contact work during this launch; -1 = empty */
-    const uint8_t *hint_in; /* N: != 0 -> the env is in `list` and the tile rounds leave it alone */
-    uint8_t *hint_out;      /* N: the same for the next launch */
+    int *ctl;             /* counters of this step (all start at 0): CTL_* below */
+    int *ctl_other;       /* counters of the next step: zeroed by this one */
+    int *list;            /* N slots: envs that need the contact path -- light from the front, heavy from the back */
     uint64_t global_offset;
     uint32_t flags;
     int cur;
@@ -177,7 +168,7 @@ struct StepParams {
 /* Per-thread tallies for the per-rollout statistics. */
 struct Tally { int done, goals_b, goals_r, contacts, overflow, envs; float ret; };
 
-__device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &P, int64_t e, Env &E, Work &W, int &hint, bool &fresh,
+__device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &P, int64_t e, Env &E, Work &W, int &load, bool &fresh,
                                              Tally &T)
 {
     float act[12];
@@ -188,9 +179,7 @@ __device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &
     act[8] = x2.x; act[9] = x2.y; act[10] = x2.z; act[11] = x2.w;
     load_env(P.A, e, E);
     StepOut out;
-    int load;
     if (!env_step(FAST, E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
-    hint = out.hint;
     store_env(P.A, e, E);
     reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
     P.done[e] = out.done;
@@ -202,44 +191,26 @@ __device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &
     return true;
 }
 
-/* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
-   lanes' solver bodies (30 fields) and first CON_FAST contacts (56 fields), field-major with stride 32
-   (conflict-free); afterwards the lanes' four new observation frames (lane-major, stride ENV_STRIDE). */
-static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
-constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
+/* The fused step is two launches, each tuned for its half of the work.
+   msoc_step_fast_kernel     streams over ALL envs, thread t of block b steps env b*128 + t in contact-free
+                             mode and its warp writes the observation rows.  No contact code is compiled into
+                             it: few registers, small shared memory, small instruction footprint -> many
+                             resident warps to hide the HBM latency.  Envs whose broad phase finds a candidate
+                             pair (~28 % in the benchmark mix) write nothing and are appended, one atomic per
+                             warp and class, to the step's contact list: light (exactly one agent x wall pair,
+                             the bulk) from the front, heavy (anything else) from the back.
+   msoc_step_contact_kernel  a persistent grid takes batches of 128 listed envs -- the heavy ones first (longest
+                             jobs first), then the light ones -- and every thread steps one of them in full
+                             mode: narrow phase, arbiter cache, 10-iteration impulse solver with bodies and
+                             contacts in shared memory; its warp writes the rows.  The divergent, latency-bound
+                             contact work therefore always runs on full warps of similar work. */
+enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
 
-/* The fused step: a persistent grid (a few blocks per SM) works through rounds of STEP_BLOCK envs.
-   tile round     thread t steps env tile*STEP_BLOCK + t in contact-free mode and its warp writes those
-                  envs' observation rows.  Envs whose broad phase finds a candidate pair decline (nothing
-                  of theirs has been written) and go to the dynamic queue in global memory.
-   contact round  every thread takes one env off a list and steps it in full mode (narrow phase, arbiter
-                  cache, 10-iteration impulse solver with bodies and contacts in shared memory); its warp
-                  writes the rows.
-   Contacts persist (an agent hugging a wall, two agents wedged in a corner), so the envs that needed
-   contact work in the previous step are known before this launch starts: whoever steps an env also
-   decides where it goes next -- the light list (one agent x wall pair), the heavy list (anything else),
-   or neither -- and sets its hint byte; tile rounds skip hinted envs without loading them.  A launch
-   therefore starts with its two lists complete, and only the few envs that START touching something in
-   this step are discovered by the tile rounds (dynamic queue).
-   Scheduling: between rounds thread 0 of a block fetches the next work item while the current round runs.
-   A full batch of the dynamic queue goes first; the lists are paced against the tile counter (a list is
-   served while its consumed fraction lags the fraction of tiles handed out, the heavy list with a lead), so
-   the slow, latency-bound contact rounds are all full, start with the launch and are spread evenly over it,
-   overlapping with the other resident blocks' memory-bound tile rounds; the remaining tiles are handed out
-   dynamically.  Blocks that run out of tiles serve what is left of the lists and the queue until all are
-   empty; no block ever waits for another one, so the grid need not be co-resident.
-   The divergent contact work always runs on full warps of similar work and a single copy of the step code
-   serves every kind of round. */
-enum { CTL_TILE = 0, CTL_DTAIL, CTL_DHEAD, CTL_LTAIL, CTL_LHEAD, CTL_HTAIL, CTL_HHEAD, CTL_WORDS = 8 };
-enum { ITEM_TILE = 0, ITEM_LIGHT, ITEM_HEAVY, ITEM_DYN, ITEM_DRAIN, ITEM_EXIT };
-#ifndef MSOC_PACE_HEAVY
-#define MSOC_PACE_HEAVY 1.15f
+constexpr int FAST_STRIDE = 89; /* floats of per-lane frame staging in the fast kernel (88, odd: no bank conflicts) */
+constexpr size_t FAST_SMEM_BYTES = (size_t)STEP_BLOCK * FAST_STRIDE * sizeof(float);
+#ifndef MSOC_FAST_MIN_BLOCKS
+#define MSOC_FAST_MIN_BLOCKS 4
 #endif
-#ifndef MSOC_PACE_LIGHT
-#define MSOC_PACE_LIGHT 1.05f
-#endif
-
-__device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 
 /* Appends the envs of the lanes with `want` set at `*tail` (one atomic per warp); slot(i) maps the i-th
    entry to its address. */
@@ -254,181 +225,9 @@ __device__ __forceinline__ void push_warp(int *tail, bool want, int env, int lan
     if (want) *slot(base + __popc(m & ((1u << lane) - 1u))) = env;
 }
 
-/* Thread 0: claims up to STEP_BLOCK envs of the dynamic queue; a partial batch only if `allow_partial`
-   (blocks that have run out of tiles).  Returns the batch size (0: nothing to take) and its first slot. */
-__device__ __forceinline__ int claim_dyn(const StepParams &P, bool allow_partial, int &first)
+/* warp reduce of the per-rollout statistics (marl-soccer.ipynb:411-429), one atomic per warp and counter */
+__device__ __forceinline__ void flush_tally(const Tally &T, double *stats, int lane)
 {
-    while (true) {
-        const int h = ld_volatile(P.ctl + CTL_DHEAD), t = ld_volatile(P.ctl + CTL_DTAIL);
-        const int avail = t - h;
-        if (avail <= 0 || (avail < STEP_BLOCK && !allow_partial)) return 0;
-        const int take = avail < STEP_BLOCK ? avail : STEP_BLOCK;
-        if (atomicCAS(P.ctl + CTL_DHEAD, h, h + take) == h) { first = h; return take; }
-    }
-}
-
-/* Thread 0: claims the next batch of a list of `total` envs if its consumed fraction does not exceed
-   `limit`.  Returns the batch size. */
-__device__ __forceinline__ int claim_list(int *head, int total, float limit, int &first)
-{
-    const int h0 = ld_volatile(head);
-    if (h0 >= total || (float)h0 > limit * (float)total) return 0;
-    const int h = atomicAdd(head, STEP_BLOCK);
-    if (h >= total) return 0;
-    first = h;
-    return total - h < STEP_BLOCK ? total - h : STEP_BLOCK;
-}
-
-struct Item { int kind, first, count; };
-
-/* Thread 0: the next work item of the block.  `drain`: the block has no tiles left and all its pushes to the
-   dynamic queue are done (decided at a barrier, never while a tile round is still running). */
-__device__ __forceinline__ Item fetch_item(const StepParams &P, int n_tiles, int n_light, int n_heavy, bool &tiles_done, bool drain)
-{
-    Item it; it.first = 0; it.count = 0;
-    if ((it.count = claim_dyn(P, false, it.first)) > 0) { it.kind = ITEM_DYN; return it; }
-    float ft = 2.0f; /* no tiles left: the lists are served unconditionally */
-    if (!tiles_done) {
-        const int handed = ld_volatile(P.ctl + CTL_TILE);
-        ft = (float)(handed < n_tiles ? handed : n_tiles) / (float)n_tiles;
-    }
-    if ((it.count = claim_list(P.ctl + CTL_HHEAD, n_heavy, MSOC_PACE_HEAVY * ft + 0.03f, it.first)) > 0) { it.kind = ITEM_HEAVY; return it; }
-    if ((it.count = claim_list(P.ctl + CTL_LHEAD, n_light, MSOC_PACE_LIGHT * ft + 0.02f, it.first)) > 0) { it.kind = ITEM_LIGHT; return it; }
-    if (!tiles_done) {
-        it.first = atomicAdd(P.ctl + CTL_TILE, 1);
-        if (it.first < n_tiles) { it.kind = ITEM_TILE; return it; }
-        tiles_done = true;
-        /* the pacing held batches back: serve them now */
-        if ((it.count = claim_list(P.ctl + CTL_HHEAD, n_heavy, 2.0f, it.first)) > 0) { it.kind = ITEM_HEAVY; return it; }
-        if ((it.count = claim_list(P.ctl + CTL_LHEAD, n_light, 2.0f, it.first)) > 0) { it.kind = ITEM_LIGHT; return it; }
-    }
-    if (!drain) { it.kind = ITEM_DRAIN; return it; }
-    /* Whatever is queued now, full batch or not.  A block leaves when the queue is empty: every env is queued
-       before its own block starts draining, so the last block to get here sees them all. */
-    it.count = claim_dyn(P, true, it.first);
-    it.kind = it.count > 0 ? ITEM_DYN : ITEM_EXIT;
-    return it;
-}
-
-__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(const __grid_constant__ StepParams P)
-{
-    extern __shared__ float s_dyn[];
-    __shared__ int s_item[3]; /* next work item of this block: kind, first, count */
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
-    const int n_tiles = (int)((P.A.n + STEP_BLOCK - 1) / STEP_BLOCK);
-    const int n_light = P.ctl[CTL_LTAIL], n_heavy = P.ctl[CTL_HTAIL]; /* final: counted by the previous launch */
-    const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
-    float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
-    bool tiles_done = false; /* thread 0: the tile counter ran past the last tile */
-    if (tid == 0) {
-        if (blockIdx.x == 0)
-            for (int i = 0; i < CTL_WORDS; i++) P.ctl_zero[i] = 0;
-        const Item it = fetch_item(P, n_tiles, n_light, n_heavy, tiles_done, false);
-        s_item[0] = it.kind; s_item[1] = it.first; s_item[2] = it.count;
-    }
-
-    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
-    float ovf_store[MAXC - CON_FAST][CON_FIELDS]; /* local memory, touched only by envs with more than CON_FAST contacts */
-    Work W;
-    W.ovf = ovf_store;
-    W.body = s_warp + lane;
-    W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
-    W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
-    W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
-#ifdef MSOC_TIMING
-    long long cyc_tile = 0, cyc_con[3] = {0, 0, 0}, t_start = clock64(); int n_tile = 0, n_con[3] = {0, 0, 0}, n_con_envs[3] = {0, 0, 0};
-    long long ph[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}}, tmc[4][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}; /* per round kind: step, frames, writer, barrier | env_step phases */
-    for (int i = 0; i < 8; i++) W.tm[i] = 0;
-#endif
-#pragma unroll 1
-    while (true) {
-        __syncthreads(); /* the item is stable: thread 0 does not write it again before the next barrier */
-        const int kind = s_item[0], ifirst = s_item[1];
-        const int icnt = s_item[2];
-        __syncthreads();
-        if (kind == ITEM_EXIT) break;
-        if (kind == ITEM_DRAIN) {
-            /* out of tiles, and every push of this block to the dynamic queue is done (barrier above) */
-            if (tid == 0) {
-                const Item it = fetch_item(P, n_tiles, n_light, n_heavy, tiles_done, true);
-                s_item[0] = it.kind; s_item[1] = it.first; s_item[2] = it.count;
-            }
-            continue;
-        }
-#ifdef MSOC_TIMING
-        const long long t0 = clock64();
-#endif
-        int64_t my_env = 0;
-        bool have;
-        if (kind == ITEM_TILE) {
-            my_env = (int64_t)ifirst * STEP_BLOCK + tid;
-            have = my_env < P.A.n && P.hint_in[my_env] == 0; /* hinted envs are on a list: not ours, not even loaded */
-        } else {
-            have = tid < icnt;
-            if (have) {
-                if (kind == ITEM_LIGHT) my_env = (int64_t)P.list[ifirst + tid];
-                else if (kind == ITEM_HEAVY) my_env = (int64_t)P.list[P.A.n - 1 - (ifirst + tid)];
-                else {
-                    int v;
-                    while ((v = ld_volatile(P.dynq + ifirst + tid)) < 0) { } /* reserved by a pusher, written any moment */
-                    P.dynq[ifirst + tid] = -1; /* empty again for the next launch */
-                    my_env = (int64_t)v;
-                }
-            }
-        }
-        /* thread 0 fetches the item after this one while the round runs (the latency of its atomics is hidden) */
-        if (tid == 0) {
-            const Item it = fetch_item(P, n_tiles, n_light, n_heavy, tiles_done, false);
-            s_item[0] = it.kind; s_item[1] = it.first; s_item[2] = it.count;
-        }
-        bool fresh = false, ok = false;
-        int hint = 0;
-#ifdef MSOC_TIMING
-        const int kind_t = kind == ITEM_TILE ? 0 : (kind == ITEM_LIGHT ? 1 : (kind == ITEM_HEAVY ? 2 : 3));
-        long long tmb[5]; for (int i = 0; i < 5; i++) tmb[i] = W.tm[i];
-        long long tp = clock64();
-#define PH(i) do { __syncwarp(); const long long n_ = clock64(); ph[kind_t][i] += n_ - tp; tp = n_; } while (0)
-#else
-#define PH(i) do { } while (0)
-#endif
-        {
-            Env E;
-            if (have) ok = step_one_env(kind == ITEM_TILE, P, my_env, E, W, hint, fresh, T);
-            __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
-            PH(0);
-            if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
-        }
-        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-        const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
-        __syncwarp();
-        PH(1);
-        if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
-        /* where the env goes in the next step; envs that declined the tile round are stepped later in this launch */
-        if (ok) P.hint_out[my_env] = (uint8_t)hint;
-        push_warp(P.ctl_next + CTL_LTAIL, ok && hint == 1, (int)my_env, lane, [&](int i) { return P.list_next + i; });
-        push_warp(P.ctl_next + CTL_HTAIL, ok && hint == 2, (int)my_env, lane, [&](int i) { return P.list_next + (P.A.n - 1 - i); });
-        push_warp(P.ctl + CTL_DTAIL, have && !ok, (int)my_env, lane, [&](int i) { return P.dynq + i; });
-        PH(2);
-#ifdef MSOC_TIMING
-        __syncthreads();
-        PH(3);
-        for (int i = 0; i < 5; i++) tmc[kind_t][i] += W.tm[i] - tmb[i];
-        { const long long dt = clock64() - t0; if (kind_t > 0) { cyc_con[kind_t - 1] += dt; n_con[kind_t - 1]++; n_con_envs[kind_t - 1] += icnt; } else { cyc_tile += dt; n_tile++; } }
-#endif
-    }
-#ifdef MSOC_TIMING
-    if (tid == 0 && (blockIdx.x % 97) == 0)
-        printf("blk %d: tile rounds %d avg %lld | light %d envs %d avg %lld | heavy %d envs %d avg %lld | dyn %d envs %d avg %lld | total %lld\n", blockIdx.x, n_tile,
-               cyc_tile / (n_tile ? n_tile : 1), n_con[0], n_con_envs[0], cyc_con[0] / (n_con[0] ? n_con[0] : 1), n_con[1], n_con_envs[1],
-               cyc_con[1] / (n_con[1] ? n_con[1] : 1), n_con[2], n_con_envs[2], cyc_con[2] / (n_con[2] ? n_con[2] : 1), clock64() - t_start);
-    if (lane == 0 && (blockIdx.x % 97) == 0)
-        for (int k = 0; k < 4; k++)
-            printf("  blk %d warp %d kind %d: step %lld frames %lld writer %lld barrier %lld | prologue %lld narrow %lld prestep %lld solver %lld cacheout %lld\n", blockIdx.x, warp, k,
-                   ph[k][0], ph[k][1], ph[k][2], ph[k][3], tmc[k][0], tmc[k][1], tmc[k][2], tmc[k][3], tmc[k][4]);
-#endif
-
-    /* per-rollout statistics (marl-soccer.ipynb:411-429): warp reduce, one atomic per warp and counter */
     int nd = T.done, gb = T.goals_b, gr = T.goals_r, nc = T.contacts, ov = T.overflow, na = T.envs;
     float ret = T.ret;
 #pragma unroll
@@ -439,13 +238,99 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_kernel(
         ret += __shfl_xor_sync(0xffffffffu, ret, o);
     }
     if (lane == 0) {
-        if (nd) { atomicAdd(P.stats + 0, (double)nd); atomicAdd(P.stats + 1, (double)ret); }
-        if (gb) atomicAdd(P.stats + 2, (double)gb);
-        if (gr) atomicAdd(P.stats + 3, (double)gr);
-        if (na) atomicAdd(P.stats + 4, (double)na);
-        if (nc) atomicAdd(P.stats + 5, (double)nc);
-        if (ov) atomicAdd(P.stats + 6, (double)ov);
+        if (nd) { atomicAdd(stats + 0, (double)nd); atomicAdd(stats + 1, (double)ret); }
+        if (gb) atomicAdd(stats + 2, (double)gb);
+        if (gr) atomicAdd(stats + 3, (double)gr);
+        if (na) atomicAdd(stats + 4, (double)na);
+        if (nc) atomicAdd(stats + 5, (double)nc);
+        if (ov) atomicAdd(stats + 6, (double)ov);
     }
+}
+
+__global__ void __launch_bounds__(STEP_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fast_kernel(const __grid_constant__ StepParams P)
+{
+    extern __shared__ float s_dyn[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
+    if (blockIdx.x == 0 && tid < CTL_WORDS) P.ctl_other[tid] = 0;
+    const int64_t my_env = (int64_t)blockIdx.x * STEP_BLOCK + tid;
+    const bool have = my_env < P.A.n;
+    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    Work W; /* never touched in contact-free mode */
+    W.ovf = nullptr; W.body = W.con = W.geom = W.old = nullptr;
+    bool fresh = false, ok = false;
+    int load = 0;
+    {
+        Env E;
+        if (have) ok = step_one_env(true, P, my_env, E, W, load, fresh, T);
+        if (ok) make_frames<22>(E, P.cfg, s_warp + lane * FAST_STRIDE);
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+    const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
+    __syncwarp();
+    if (mask) write_obs_tile<FAST_STRIDE>(reinterpret_cast<const float2 *>(P.obs_in), reinterpret_cast<float2 *>(P.obs_out), s_warp, mask,
+                                          fmask, my_env, lane);
+    const bool declined = have && !ok;
+    push_warp(P.ctl + CTL_LIGHT, declined && load == 0, (int)my_env, lane, [&](int i) { return P.list + i; });
+    push_warp(P.ctl + CTL_HEAVY, declined && load != 0, (int)my_env, lane, [&](int i) { return P.list + (P.A.n - 1 - i); });
+    flush_tally(T, P.stats, lane);
+}
+
+/* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
+   lanes' solver bodies (30 fields) and first CON_FAST contacts (56 fields), field-major with stride 32
+   (conflict-free); afterwards the lanes' four new observation frames (lane-major, stride ENV_STRIDE). */
+static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
+constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
+
+__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
+{
+    extern __shared__ float s_dyn[];
+    __shared__ int s_batch[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
+    const int n_light = P.ctl[CTL_LIGHT], n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
+    const int heavy_batches = (n_heavy + STEP_BLOCK - 1) / STEP_BLOCK, light_batches = (n_light + STEP_BLOCK - 1) / STEP_BLOCK;
+    const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
+    float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
+
+    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    float ovf_store[MAXC - CON_FAST][CON_FIELDS]; /* local memory, touched only by envs with more than CON_FAST contacts */
+    Work W;
+    W.ovf = ovf_store;
+    W.body = s_warp + lane;
+    W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
+    W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
+    W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
+#pragma unroll 1
+    while (true) {
+        /* next batch: heavy batches first (longest jobs first), handed out dynamically */
+        if (tid == 0) {
+            int b = atomicAdd(P.ctl + CTL_NEXT_HEAVY, 1), heavy = 1;
+            if (b >= heavy_batches) { b = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1); heavy = 0; if (b >= light_batches) b = -1; }
+            s_batch[0] = b; s_batch[1] = heavy;
+        }
+        __syncthreads();
+        const int b = s_batch[0], heavy = s_batch[1];
+        __syncthreads();
+        if (b < 0) break;
+        const int idx = b * STEP_BLOCK + tid;
+        const bool have = idx < (heavy ? n_heavy : n_light);
+        int64_t my_env = 0;
+        if (have) my_env = (int64_t)(heavy ? P.list[P.A.n - 1 - idx] : P.list[idx]);
+        bool fresh = false, ok = false;
+        int load = 0;
+        {
+            Env E;
+            if (have) ok = step_one_env(false, P, my_env, E, W, load, fresh, T);
+            __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
+            if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
+        __syncwarp();
+        if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
+    }
+    flush_tally(T, P.stats, lane);
 }
 
 /* ------------------------------------------------------------------------------------- reset */
@@ -611,9 +496,8 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     const size_t o_rew = take(n * 2 * sizeof(float)), o_done = take(n), o_goal = take(n), o_mask = take(n);
     const size_t o_score = take(n * 2 * sizeof(int32_t));
     const size_t o_stats = take(8 * sizeof(double));
-    const size_t o_tile = take(3 * 8 * sizeof(int));
-    const size_t o_list0 = take(n * sizeof(int)), o_list1 = take(n * sizeof(int)), o_gq = take(n * sizeof(int));
-    const size_t o_hint0 = take(n), o_hint1 = take(n);
+    const size_t o_tile = take(2 * 4 * sizeof(int));
+    const size_t o_list = take(n * sizeof(int));
     const size_t total = off;
 
     ce = cudaMalloc(&h->slab, total);
@@ -639,17 +523,14 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     h->d_score = (int32_t *)(base + o_score);
     h->d_stats = (double *)(base + o_stats);
     h->d_ctl = (int *)(base + o_tile);
-    h->d_list[0] = (int *)(base + o_list0); h->d_list[1] = (int *)(base + o_list1);
-    h->d_dynq = (int *)(base + o_gq);
-    h->d_hint[0] = (uint8_t *)(base + o_hint0); h->d_hint[1] = (uint8_t *)(base + o_hint1);
-    ce = cudaMemset(h->d_dynq, 0xFF, n * sizeof(int)); /* every slot empty (-1) */
-    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: cudaMemset", ce); }
+    h->d_list = (int *)(base + o_list);
 
-    ce = cudaFuncSetAttribute(msoc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)STEP_SMEM_BYTES);
+    ce = cudaFuncSetAttribute(msoc_step_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
     if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_kernel, STEP_BLOCK, STEP_SMEM_BYTES);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, STEP_BLOCK, STEP_SMEM_BYTES);
     if (const char *ov = getenv("MSOC_BLOCKS_PER_SM")) { /* tuning experiments only */
         const int v = atoi(ov);
         if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v;
@@ -703,16 +584,15 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_in = d_obs_in; P.obs_out = d_obs_out;
     P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
     P.global_offset = h->global_offset; P.flags = flags; P.cur = h->cur;
-    const int r0 = (int)(h->step_seq % 3), r1 = (int)((h->step_seq + 1) % 3), r2 = (int)((h->step_seq + 2) % 3);
-    const int b0 = (int)(h->step_seq & 1), b1 = b0 ^ 1;
-    P.ctl = h->d_ctl + 8 * r0; P.ctl_next = h->d_ctl + 8 * r1; P.ctl_zero = h->d_ctl + 8 * r2;
-    P.list = h->d_list[b0]; P.list_next = h->d_list[b1]; P.dynq = h->d_dynq;
-    P.hint_in = h->d_hint[b0]; P.hint_out = h->d_hint[b1];
-    h->step_seq++;
+    P.ctl = h->d_ctl + 4 * h->step_parity; P.ctl_other = h->d_ctl + 4 * (h->step_parity ^ 1); P.list = h->d_list;
+    h->step_parity ^= 1;
     const int64_t n_tiles = (h->n + STEP_BLOCK - 1) / STEP_BLOCK;
+    msoc_step_fast_kernel<<<(unsigned)n_tiles, STEP_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    msoc_step_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    msoc_step_contact_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     g_launches++;
     h->cur ^= 1;
     CUDA_TRY(cudaGetLastError());

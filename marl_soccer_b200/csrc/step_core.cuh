@@ -54,7 +54,10 @@ constexpr int SOLVER_ITERS = 10;                  /* cpSpace iterations default 
 
 constexpr int N_AGENTS = 4, BALL = 4, STATIC_BODY = 5;
 constexpr int FRAME = 22, OBS = 66;
-constexpr int MAXC = 24;      /* contacts solved per env and step */
+#ifndef MSOC_MAXC
+#define MSOC_MAXC 24
+#endif
+constexpr int MAXC = MSOC_MAXC;      /* contacts solved per env and step */
 constexpr int MAX_CACHE = 32; /* == MSOC_MAX_CACHE */
 
 /* pair ids (shared with the oracle and include/msoc.h) */
@@ -910,7 +913,6 @@ struct StepOut {
     float finished_return; /* blue return of the episode that ended on this step */
     int n_contacts, overflow;
     int32_t score_b, score_r; /* info["score"] of this step (before any auto-reset) */
-    uint8_t hint;             /* scheduling hint for the next step: 0 = expect no contact work, 1 = light, 2 = heavy */
 };
 
 /* Full reset of one env (Game.reset, game/game.py:76-118): bodies re-created (all velocities,
@@ -1038,12 +1040,16 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
 #else
     const bool contact_path = any_candidate || old_count != 0;
 #endif
-    /* work class of an env that needs the contact path, used to batch envs of similar contact work:
-       0 = exactly one candidate pair and it is agent x segment (the bulk: an agent touching a wall),
-       1 = anything else (several pairs, agent x agent, ball) */
-    load = (popc32(m_as) == 1 && (m_aa | m_ba | m_bw) == 0u) ? 0 : 1;
-    if (FAST && contact_path) return false;
+    load = 0;
     const bool run_contacts = !FAST && contact_path;
+    if (FAST) {
+        if (contact_path) {
+            /* work class for the contact queues: 0 = exactly one candidate pair and it is agent x segment
+               (the bulk: an agent touching a wall), 1 = anything else (several pairs, agent x agent, ball) */
+            load = (popc32(m_as) == 1 && (m_aa | m_ba | m_bw) == 0u) ? 0 : 1;
+            return false;
+        }
+    }
     if (!contact_path && old_count != 0) {
         /* nothing can touch this step, but the env still carries arbiters of contacts that ended
            less than collision_persistence (3) steps ago: age them (cpSpaceArbiterSetFilter) */
@@ -1290,7 +1296,6 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     out.reward = r; out.done = done ? 1 : 0; out.goal = (int8_t)goal;
     out.fresh_episode = false; out.finished_return = 0.0f;
     out.n_contacts = n_contacts; out.overflow = overflow;
-    out.hint = (uint8_t)(any_candidate ? 1 + load : (new_count > 0 ? 1 : 0));
     out.score_b = E.score_b; out.score_r = E.score_r;
     if (done) {
         out.finished_return = E.ep_return;
