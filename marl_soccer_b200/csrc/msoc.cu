@@ -58,7 +58,7 @@ struct msoc_handle {
     SimCfg cfg;
     Arrays A;
     int cur; /* which half of the ping-pong arbiter cache is current */
-    int sm_count, blocks_per_sm; /* persistent grid of the contact kernel */
+    int sm_count, blocks_per_sm, light_blocks_per_sm; /* persistent grids of the contact and light kernels */
     void *slab;
     /* internal I/O buffers of the host-buffer API */
     float *d_obs, *d_act, *d_rew;
@@ -168,7 +168,7 @@ struct StepParams {
 /* Per-thread tallies for the per-rollout statistics. */
 struct Tally { int done, goals_b, goals_r, contacts, overflow, envs; float ret; };
 
-__device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &P, int64_t e, Env &E, Work &W, int &load, bool &fresh,
+__device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P, int64_t e, Env &E, Work &W, int &load, bool &fresh,
                                              Tally &T)
 {
     float act[12];
@@ -179,7 +179,7 @@ __device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &
     act[8] = x2.x; act[9] = x2.y; act[10] = x2.z; act[11] = x2.w;
     load_env(P.A, e, E);
     StepOut out;
-    if (!env_step(FAST, E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
+    if (!env_step(MODE, E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
     store_env(P.A, e, E);
     reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
     P.done[e] = out.done;
@@ -191,7 +191,7 @@ __device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &
     return true;
 }
 
-/* The fused step is two launches, each tuned for its half of the work.
+/* The fused step is three launches, each tuned for its share of the work.
    msoc_step_fast_kernel     streams over ALL envs, thread t of block b steps env b*128 + t in contact-free
                              mode and its warp writes the observation rows.  No contact code is compiled into
                              it: few registers, small shared memory, small instruction footprint -> many
@@ -199,11 +199,14 @@ __device__ __forceinline__ bool step_one_env(const bool FAST, const StepParams &
                              pair (~28 % in the benchmark mix) write nothing and are appended, one atomic per
                              warp and class, to the step's contact list: light (exactly one agent x wall pair,
                              the bulk) from the front, heavy (anything else) from the back.
-   msoc_step_contact_kernel  a persistent grid takes batches of 128 listed envs -- the heavy ones first (longest
-                             jobs first), then the light ones -- and every thread steps one of them in full
-                             mode: narrow phase, arbiter cache, 10-iteration impulse solver with bodies and
-                             contacts in shared memory; its warp writes the rows.  The divergent, latency-bound
-                             contact work therefore always runs on full warps of similar work. */
+   msoc_step_light_kernel    batches of 128 light envs, thread per env: one narrow-phase call and a register-only
+                             single-body impulse solver (at most two contacts); again no solver scratch.
+   msoc_step_contact_kernel  a persistent grid takes batches of 128 heavy envs and every thread steps one of
+                             them in full mode: narrow phase over all candidate pairs, arbiter cache,
+                             10-iteration impulse solver with bodies and contacts in shared memory; its warp
+                             writes the rows.
+   The divergent, latency-bound contact work therefore always runs on full warps of similar work, and each
+   kind of work gets the register / shared-memory budget (hence the occupancy) that suits it. */
 enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
 
 constexpr int FAST_STRIDE = 89; /* floats of per-lane frame staging in the fast kernel (88, odd: no bank conflicts) */
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     int load = 0;
     {
         Env E;
-        if (have) ok = step_one_env(true, P, my_env, E, W, load, fresh, T);
+        if (have) ok = step_one_env(MODE_FAST, P, my_env, E, W, load, fresh, T);
         if (ok) make_frames<22>(E, P.cfg, s_warp + lane * FAST_STRIDE);
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, ok);
@@ -276,20 +279,64 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     flush_tally(T, P.stats, lane);
 }
 
+/* Light envs (exactly one agent x wall candidate pair, ~82 % of the contact envs): thread t of a batch steps
+   one listed env with the register-only single-body solver of step_core.cuh (MODE_LIGHT).  Like the fast
+   kernel it needs no solver scratch: shared memory only stages the frames. */
+#ifndef MSOC_LIGHT_MIN_BLOCKS
+#define MSOC_LIGHT_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(STEP_BLOCK, MSOC_LIGHT_MIN_BLOCKS) msoc_step_light_kernel(const __grid_constant__ StepParams P)
+{
+    extern __shared__ float s_dyn[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
+    const int n_light = P.ctl[CTL_LIGHT]; /* final: the fast kernel has finished */
+    const int batches = (n_light + STEP_BLOCK - 1) / STEP_BLOCK;
+    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    Work W; /* never touched in light mode */
+    W.ovf = nullptr; W.body = W.con = W.geom = W.old = nullptr;
+#pragma unroll 1
+    for (int b = (int)blockIdx.x; b < batches; b += (int)gridDim.x) {
+        const int idx = b * STEP_BLOCK + tid;
+        const bool have = idx < n_light;
+        const int64_t my_env = have ? (int64_t)P.list[idx] : 0;
+        bool fresh = false, ok = false;
+        int load = 0;
+        {
+            Env E;
+            if (have) ok = step_one_env(MODE_LIGHT, P, my_env, E, W, load, fresh, T);
+            if (ok) make_frames<22>(E, P.cfg, s_warp + lane * FAST_STRIDE);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
+        __syncwarp();
+        if (mask) write_obs_tile<FAST_STRIDE>(reinterpret_cast<const float2 *>(P.obs_in), reinterpret_cast<float2 *>(P.obs_out), s_warp,
+                                              mask, fmask, my_env, lane);
+        __syncwarp(); /* the staging area is rewritten by the next batch */
+    }
+    flush_tally(T, P.stats, lane);
+}
+
 /* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
    lanes' solver bodies (30 fields) and first CON_FAST contacts (56 fields), field-major with stride 32
    (conflict-free); afterwards the lanes' four new observation frames (lane-major, stride ENV_STRIDE). */
 static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
 constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
 
+#ifdef MSOC_WARP_TIMING
+__device__ long long g_wb[8192 * 4];
+extern "C" int msoc_debug_wb(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_wb, sizeof g_wb); }
+#endif
+#ifndef MSOC_MERGE_LIGHT
+#define MSOC_MERGE_LIGHT 0 /* 1: the contact kernel also takes the light batches once the heavy ones are handed out */
+#endif
 __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
-    __shared__ int s_batch[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
-    const int n_light = P.ctl[CTL_LIGHT], n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
-    const int heavy_batches = (n_heavy + STEP_BLOCK - 1) / STEP_BLOCK, light_batches = (n_light + STEP_BLOCK - 1) / STEP_BLOCK;
+    const int n_light = MSOC_MERGE_LIGHT ? P.ctl[CTL_LIGHT] : 0, n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
+    const int heavy_batches = (n_heavy + 31) / 32, light_batches = (n_light + 31) / 32;
     const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
     float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
 
@@ -301,27 +348,36 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact
     W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
     W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
+    bool heavy = true; /* warp-uniform: still taking heavy batches */
 #pragma unroll 1
     while (true) {
-        /* next batch: heavy batches first (longest jobs first), handed out dynamically */
-        if (tid == 0) {
-            int b = atomicAdd(P.ctl + CTL_NEXT_HEAVY, 1), heavy = 1;
-            if (b >= heavy_batches) { b = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1); heavy = 0; if (b >= light_batches) b = -1; }
-            s_batch[0] = b; s_batch[1] = heavy;
+        /* every WARP takes its own batches of 32 envs (the scratch is per warp, so the warps of a block never wait
+           for each other): the heavy ones first -- the batches differ a lot in length --, handed out dynamically */
+        int b = 0;
+        if (heavy) {
+            if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_HEAVY, 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= heavy_batches) heavy = false;
         }
-        __syncthreads();
-        const int b = s_batch[0], heavy = s_batch[1];
-        __syncthreads();
-        if (b < 0) break;
-        const int idx = b * STEP_BLOCK + tid;
+        if (!heavy) {
+            if (light_batches == 0) break;
+            if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= light_batches) break;
+        }
+        const int idx = b * 32 + lane;
         const bool have = idx < (heavy ? n_heavy : n_light);
         int64_t my_env = 0;
         if (have) my_env = (int64_t)(heavy ? P.list[P.A.n - 1 - idx] : P.list[idx]);
+#ifdef MSOC_WARP_TIMING
+        const long long wt0 = clock64(); const int c0 = T.contacts;
+#endif
         bool fresh = false, ok = false;
         int load = 0;
         {
             Env E;
-            if (have) ok = step_one_env(false, P, my_env, E, W, load, fresh, T);
+            if (have) ok = heavy ? step_one_env(MODE_FULL, P, my_env, E, W, load, fresh, T)
+                                 : step_one_env(MODE_LIGHT, P, my_env, E, W, load, fresh, T);
             __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
             if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
         }
@@ -329,6 +385,14 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact
         const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
         __syncwarp();
         if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
+        __syncwarp();
+#ifdef MSOC_WARP_TIMING
+        {
+            int nc = T.contacts - c0, mx = nc, sum = nc;
+            for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+            if (lane == 0 && heavy && b < 8192) { g_wb[b * 4] = clock64() - wt0; g_wb[b * 4 + 1] = mx; g_wb[b * 4 + 2] = sum; g_wb[b * 4 + 3] = (long long)blockIdx.x; }
+        }
+#endif
     }
     flush_tally(T, P.stats, lane);
 }
@@ -528,6 +592,10 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     ce = cudaFuncSetAttribute(msoc_step_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(msoc_step_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
+    if (ce == cudaSuccess)
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, STEP_BLOCK, FAST_SMEM_BYTES);
     if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, STEP_BLOCK, STEP_SMEM_BYTES);
@@ -590,6 +658,12 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     msoc_step_fast_kernel<<<(unsigned)n_tiles, STEP_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+#if !MSOC_MERGE_LIGHT
+    const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
+    msoc_step_light_kernel<<<(unsigned)(n_tiles < light_resident ? n_tiles : light_resident), STEP_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+#endif
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
     msoc_step_contact_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(P);

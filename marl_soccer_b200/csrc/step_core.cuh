@@ -933,14 +933,18 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
 }
 
 /* One env-step (everything except the observation frames, which the caller builds from E afterwards).
-   FAST = true is the contact-free mode used by the kernel's first pass: it returns false -- leaving E
+   MODE_FAST is the contact-free mode used by the kernel's first pass: it returns false -- leaving E
    meaningless and every array untouched -- as soon as the broad phase finds a candidate pair or the env
    still carries cached arbiters; such envs are then stepped in full mode (FAST = false, always returns
    true) on a compacted set of threads.  (A runtime flag, not a template: one copy of the code.)  `load` is the work class of a
    declined env (0 light, 1 heavy; see below), used to batch envs of similar contact work.  W is only touched when !FAST. */
-MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e,
+enum { MODE_FULL = 0, MODE_FAST = 1, MODE_LIGHT = 2 };
+MSOC_HD float sel4(const float *a, int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
+
+MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e,
                       uint64_t gidx, uint32_t step_flags, Work &W, StepOut &out, int &load)
 {
+    const bool FAST = MODE == MODE_FAST, LIGHT = MODE == MODE_LIGHT;
 #ifdef MSOC_TIMING
     long long tk = MSOC_CLOCK();
 #endif
@@ -1041,7 +1045,8 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
     const bool contact_path = any_candidate || old_count != 0;
 #endif
     load = 0;
-    const bool run_contacts = !FAST && contact_path;
+    const bool run_contacts = MODE == MODE_FULL && contact_path;
+    const bool run_light = LIGHT && contact_path;
     if (FAST) {
         if (contact_path) {
             /* work class for the contact queues: 0 = exactly one candidate pair and it is agent x segment
@@ -1119,6 +1124,11 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
         }
     }
 
+    /* light mode: the one agent that may touch a wall; its pre-update velocity feeds the arbiter pre-step */
+    const int l_idx = run_light ? ctz32(m_as) : 0, l_i = l_idx >> 3;
+    float l_ovx = 0.0f, l_ovy = 0.0f, l_ow = 0.0f;
+    if (run_light) { l_ovx = sel4(E.vx, l_i); l_ovy = sel4(E.vy, l_i); l_ow = sel4(E.w, l_i); }
+
     /* ---- cpBodyUpdateVelocity (gravity 0, damping 1) + the reference's custom velocity functions
        (game/entities.py:19-28 agent, :69-77 ball): friction multiplier, max_velocity clamp.
        (Chipmunk runs the arbiter pre-step before this; it only reads the parked old velocities.) */
@@ -1133,6 +1143,116 @@ MSOC_HD bool env_step(const bool FAST, Env &E, const float *act, const SimCfg &c
         const float l2 = vx * vx + vy * vy;
         if (l2 > c.max_velocity * c.max_velocity) { const float s_ = c.max_velocity * rsqrt_f(l2); vx *= s_; vy *= s_; }
         E.vx[i] = vx; E.vy[i] = vy;
+    }
+
+    if (run_light) {
+        /* ---- light mode: exactly one candidate pair, agent l_i x static segment.  The same arithmetic as
+           the general path below (narrow phase, arbiter cache, pre-step, warm start, 10 iterations, cache
+           write-out) for a single dynamic body and at most two contacts, entirely in registers. */
+        const uint32_t *oi_ = A.cache_info[cur]; const float *ojn_ = A.cache_jn[cur], *ojt_ = A.cache_jt[cur];
+        uint32_t *ni_ = A.cache_info[cur ^ 1]; float *njn_ = A.cache_jn[cur ^ 1], *njt_ = A.cache_jt[cur ^ 1];
+        Manifold m;
+        const Seg g = get_segment(l_idx & 7);
+        collide_segment_box(g, mk(sel4(E.px, l_i), sel4(E.py, l_i)), sel4(cs, l_i), sel4(sn, l_i), m);
+        n_contacts = m.count;
+        if (m.count > 0) {
+            /* cpArbiterUpdate: accumulated impulses of equal-key contacts, first-contact state */
+            bool first = true;
+            float jn0 = 0.0f, jt0 = 0.0f, jn1 = 0.0f, jt1 = 0.0f;
+            for (int j = 0; j < old_count; j++) {
+                const int64_t oi = (int64_t)j * A.n + e;
+                const uint32_t info = oi_[oi];
+                if ((int)(info & 63u) != l_idx) continue;
+                if (((info >> 10) & 3u) == 0u) first = false;
+                const int key = (int)((info >> 6) & 15u);
+                const float ojn = ojn_[oi], ojt = ojt_[oi];
+                if (key == m.key[0]) { jn0 = ojn; jt0 = ojt; }
+                if (m.count > 1 && key == m.key[1]) { jn1 = ojn; jt1 = ojt; }
+            }
+            const bool two = m.count > 1;
+            const float nx = m.n.x, ny = m.n.y;
+            const V2 tng = vperp(m.n);
+            const float mb = c.agent_minv, ib = c.agent_iinv;
+            const float u = ((l_idx & 7) < 6) ? U_AGENT_WALL : U_AGENT_GOALLINE;
+            /* contact records: lever arm of the agent (static side: none), cpArbiterPreStep */
+            const float rn0 = vcross(m.p2[0], m.n), rt0 = vcross(m.p2[0], tng);
+            const float rn1 = two ? vcross(m.p2[1], m.n) : 0.0f, rt1 = two ? vcross(m.p2[1], tng) : 0.0f;
+            const float nM0 = 1.0f / (mb + ib * rn0 * rn0), tM0 = 1.0f / (mb + ib * rt0 * rt0);
+            const float nM1 = 1.0f / (mb + ib * rn1 * rn1), tM1 = 1.0f / (mb + ib * rt1 * rt1);
+            const float bias0 = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[0] - m.p1[0], m.n) + SLOP);
+            const float bias1 = two ? -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[1] - m.p1[1], m.n) + SLOP) : 0.0f;
+            const float bnc0 = (l_ovx * nx + l_ovy * ny + l_ow * rn0) * E_AGENT_SEG;
+            const float bnc1 = (l_ovx * nx + l_ovy * ny + l_ow * rn1) * E_AGENT_SEG;
+            float vx = sel4(E.vx, l_i), vy = sel4(E.vy, l_i), w = sel4(E.w, l_i), bx = 0.0f, by = 0.0f, bw = 0.0f;
+            /* cpArbiterApplyCachedImpulse (skipped in an arbiter's first step) */
+            if (!first) {
+                { const float jx = nx * jn0 - ny * jt0, jy = ny * jn0 + nx * jt0;
+                  vx += jx * mb; vy += jy * mb; w += ib * (rn0 * jn0 + rt0 * jt0); }
+                if (two) { const float jx = nx * jn1 - ny * jt1, jy = ny * jn1 + nx * jt1;
+                  vx += jx * mb; vy += jy * mb; w += ib * (rn1 * jn1 + rt1 * jt1); }
+            }
+            /* cpArbiterApplyImpulse x 10 */
+            float jb0 = 0.0f, jb1 = 0.0f;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            for (int it = 0; it < SOLVER_ITERS; it++) {
+                {
+                    const float vrn = vx * nx + vy * ny + w * rn0;
+                    const float vrt = vy * nx - vx * ny + w * rt0;
+                    const float vbn = bx * nx + by * ny + bw * rn0;
+                    const float jbN = fmaxf(jb0 + (bias0 - vbn) * nM0, 0.0f);
+                    const float jnN = fmaxf(jn0 - (bnc0 + vrn) * nM0, 0.0f);
+                    const float jtMax = u * jnN;
+                    const float jtN = fminf(fmaxf(jt0 - vrt * tM0, -jtMax), jtMax);
+                    const float djb = jbN - jb0, djn = jnN - jn0, djt = jtN - jt0;
+                    jb0 = jbN; jn0 = jnN; jt0 = jtN;
+                    const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+                    bx += nx * djb * mb; by += ny * djb * mb; bw += ib * rn0 * djb;
+                    vx += jx * mb; vy += jy * mb; w += ib * (rn0 * djn + rt0 * djt);
+                }
+                if (two) {
+                    const float vrn = vx * nx + vy * ny + w * rn1;
+                    const float vrt = vy * nx - vx * ny + w * rt1;
+                    const float vbn = bx * nx + by * ny + bw * rn1;
+                    const float jbN = fmaxf(jb1 + (bias1 - vbn) * nM1, 0.0f);
+                    const float jnN = fmaxf(jn1 - (bnc1 + vrn) * nM1, 0.0f);
+                    const float jtMax = u * jnN;
+                    const float jtN = fminf(fmaxf(jt1 - vrt * tM1, -jtMax), jtMax);
+                    const float djb = jbN - jb1, djn = jnN - jn1, djt = jtN - jt1;
+                    jb1 = jbN; jn1 = jnN; jt1 = jtN;
+                    const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+                    bx += nx * djb * mb; by += ny * djb * mb; bw += ib * rn1 * djb;
+                    vx += jx * mb; vy += jy * mb; w += ib * (rn1 * djn + rt1 * djt);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k == l_i) { E.vx[k] = vx; E.vy[k] = vy; E.w[k] = w; E.vbx[k] = bx; E.vby[k] = by; E.wb[k] = bw; }
+            /* this step's contacts open the arbiter cache of the next step (age 0) */
+            {
+                const int64_t o = e; /* slot 0 */
+                ni_[o] = (uint32_t)l_idx | ((uint32_t)m.key[0] << 6); njn_[o] = jn0; njt_[o] = jt0;
+                new_count = 1;
+            }
+            if (two) {
+                const int64_t o = A.n + e; /* slot 1 */
+                ni_[o] = (uint32_t)l_idx | ((uint32_t)m.key[1] << 6); njn_[o] = jn1; njt_[o] = jt1;
+                new_count = 2;
+            }
+        }
+        /* then the untouched arbiters younger than collision_persistence (3) */
+        for (int j = 0; j < old_count; j++) {
+            const int64_t oi = (int64_t)j * A.n + e;
+            const uint32_t info = oi_[oi];
+            const uint32_t age = (info >> 10) & 3u;
+            if ((m.count > 0 && (int)(info & 63u) == l_idx) || age >= 2u) continue;
+            if (new_count >= MAX_CACHE) { overflow++; continue; }
+            const int64_t o = (int64_t)new_count * A.n + e;
+            ni_[o] = (info & 1023u) | ((age + 1u) << 10);
+            njn_[o] = ojn_[oi]; njt_[o] = ojt_[oi];
+            new_count++;
+        }
     }
 
     MSOC_TICK(W, 0, tk); /* prologue .. velocity update */
