@@ -69,6 +69,8 @@ struct msoc_handle {
     int *d_ctl;  /* 2 x CTL_WORDS counters of the step kernels, alternating between steps */
     int *d_list; /* n ints: contact list of the step in flight */
     int step_parity;
+    cudaStream_t aux_stream;        /* the light kernel runs here, beside the heavy contact kernel */
+    cudaEvent_t ev_listed, ev_light; /* fork after the fast kernel / join after the light kernel */
     void *d_stage; size_t stage_bytes; /* get/set_state staging */
 };
 
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     const bool have = my_env < P.A.n;
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
     Work W; /* never touched in contact-free mode */
-    W.ovf = nullptr; W.body = W.con = W.geom = W.old = nullptr;
+    W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
     bool fresh = false, ok = false;
     int load = 0;
     {
@@ -294,9 +296,17 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_LIGHT_MIN_BLOCKS) msoc_step_l
     const int batches = (n_light + STEP_BLOCK - 1) / STEP_BLOCK;
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
     Work W; /* never touched in light mode */
-    W.ovf = nullptr; W.body = W.con = W.geom = W.old = nullptr;
+    W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
+    __shared__ int s_batch;
 #pragma unroll 1
-    for (int b = (int)blockIdx.x; b < batches; b += (int)gridDim.x) {
+    while (true) {
+        /* batches are handed out dynamically: this kernel runs beside the heavy contact kernel and its blocks
+           start whenever an SM has room for them */
+        if (tid == 0) s_batch = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1);
+        __syncthreads();
+        const int b = s_batch;
+        __syncthreads();
+        if (b >= batches) break;
         const int idx = b * STEP_BLOCK + tid;
         const bool have = idx < n_light;
         const int64_t my_env = have ? (int64_t)P.list[idx] : 0;
@@ -318,8 +328,10 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_LIGHT_MIN_BLOCKS) msoc_step_l
 }
 
 /* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
-   lanes' solver bodies (30 fields) and first CON_FAST contacts (56 fields), field-major with stride 32
-   (conflict-free); afterwards the lanes' four new observation frames (lane-major, stride ENV_STRIDE). */
+   lanes' solver bodies (30 fields, field-major with stride 32: conflict-free), the warp's pool of
+   32 x CON_FAST contact records (15 fields, field-major; an env takes as many records as it has contacts),
+   the parked poses and the preloaded arbiter cache entries; afterwards the lanes' four new observation
+   frames (lane-major, stride ENV_STRIDE). */
 static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
 constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
 
@@ -333,6 +345,7 @@ extern "C" int msoc_debug_wb(long long *out) { return (int)cudaMemcpyFromSymbol(
 __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
+    __shared__ int s_pool_count[WARPS_PER_BLOCK];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
     const int n_light = MSOC_MERGE_LIGHT ? P.ctl[CTL_LIGHT] : 0, n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
@@ -345,7 +358,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact
     Work W;
     W.ovf = ovf_store;
     W.body = s_warp + lane;
-    W.con = s_warp + BODY_FIELDS * 5 * 32 + lane;
+    W.pool = s_warp + BODY_FIELDS * 5 * 32; /* shared by the warp's lanes */
+    W.pool_count = &s_pool_count[warp];
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
     W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
     bool heavy = true; /* warp-uniform: still taking heavy batches */
@@ -374,6 +388,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact
 #endif
         bool fresh = false, ok = false;
         int load = 0;
+        if (lane == 0) *W.pool_count = 0; /* the warp's contact pool is empty */
+        __syncwarp();
         {
             Env E;
             if (have) ok = heavy ? step_one_env(MODE_FULL, P, my_env, E, W, load, fresh, T)
@@ -606,6 +622,10 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) {
         cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
     }
+    ce = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_listed, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_light, cudaEventDisableTiming);
+    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: stream/event", ce); }
     msoc_init_kernel<<<(unsigned)((n_envs + 255) / 256), 256>>>(A, seed);
     g_launches++;
     /* Game.__init__ -> setup_field -> reset(): first spawn in the default random mode */
@@ -623,6 +643,9 @@ int msoc_destroy(msoc_handle *h)
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->ev_listed) cudaEventDestroy(h->ev_listed);
+    if (h->ev_light) cudaEventDestroy(h->ev_light);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     cudaFree(h->slab);
     delete h;
     return MSOC_OK;
@@ -658,16 +681,27 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     msoc_step_fast_kernel<<<(unsigned)n_tiles, STEP_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-#if !MSOC_MERGE_LIGHT
-    const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
-    msoc_step_light_kernel<<<(unsigned)(n_tiles < light_resident ? n_tiles : light_resident), STEP_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-#endif
+    /* The two contact kernels only depend on the fast kernel's list.  The heavy one (few, long, latency-bound
+       batches: one per warp) goes first and stays on the caller's stream; the light one runs beside it on the
+       handle's own stream and fills the SMs as the heavy blocks drain.  The caller's stream then waits for it. */
+    cudaStream_t st = (cudaStream_t)stream;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    msoc_step_contact_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+#if !MSOC_MERGE_LIGHT
+    CUDA_TRY(cudaEventRecord(h->ev_listed, st));
+#endif
+    msoc_step_contact_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, st>>>(P);
     g_launches++;
+    CUDA_TRY(cudaGetLastError());
+#if !MSOC_MERGE_LIGHT
+    CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_listed, 0));
+    const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
+    msoc_step_light_kernel<<<(unsigned)(n_tiles < light_resident ? n_tiles : light_resident), STEP_BLOCK, FAST_SMEM_BYTES, h->aux_stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev_light, h->aux_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_light, 0));
+#endif
     h->cur ^= 1;
     CUDA_TRY(cudaGetLastError());
     return MSOC_OK;

@@ -627,12 +627,12 @@ MSOC_HD void collide_ball_segment(const Seg &g, V2 c, Manifold &m)
 #define MSOC_CON_FAST 4
 #endif
 constexpr int CON_FAST = MSOC_CON_FAST; /* contacts per env held in shared memory */
-constexpr int CON_FIELDS = 14;
+constexpr int CON_FIELDS = 15; /* 14 solver fields + the link to the env's next contact */
 constexpr int BODY_FIELDS = 6; /* vx vy w bias_x bias_y bias_w, for the 5 dynamic bodies */
 /* contact record: normal, lever arms as scalars (rn = r x n, rt = r x perp(n)), effective masses,
    bounce (restitution e until the pre-step), bias (separation until the pre-step), accumulated
    impulses, meta = a | b<<3 | pair<<6 | key<<12 | first<<16 */
-enum { CF_NX, CF_NY, CF_RN1, CF_RT1, CF_RN2, CF_RT2, CF_NMASS, CF_TMASS, CF_BOUNCE, CF_BIAS, CF_JN, CF_JT, CF_JB, CF_META };
+enum { CF_NX, CF_NY, CF_RN1, CF_RT1, CF_RN2, CF_RT2, CF_NMASS, CF_TMASS, CF_BOUNCE, CF_BIAS, CF_JN, CF_JT, CF_JB, CF_META, CF_NEXT };
 enum { BF_VX, BF_VY, BF_W, BF_BX, BF_BY, BF_BW };
 #if defined(__CUDA_ARCH__)
 constexpr int SCR = 32; /* stride between consecutive scratch elements of one lane (shared memory, lane-interleaved) */
@@ -669,12 +669,15 @@ constexpr int SCRATCH_WORDS = BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WOR
 
 struct Work {
     float *body; /* field f of body i: body[f*BODY_FS + i*SCR] */
-    float *con;  /* field f of contact k < CON_FAST: con[f*CON_FS + k*SCR] */
+    float *pool; /* contact records of the whole warp: field f of slot s: pool[f*CON_FS + s], CON_FS slots handed out on demand
+                    (an env takes as many as it has contacts; on the average that is far fewer than CON_FAST per lane) */
+    int *pool_count; /* slots handed out so far (shared by the warp) */
     float *geom; /* word g: geom[g*SCR] */
     float *old;  /* preloaded cache entry j < OLD_FAST: info old[j*SCR] (bits), jn old[(OLD_FAST+j)*SCR], jt old[(2*OLD_FAST+j)*SCR] */
-    float (*ovf)[CON_FIELDS]; /* contacts CON_FAST.. (rare): caller-provided array of MAXC - CON_FAST records, field stride 1
-                                 (a pointer, so that the scalar members of this struct stay in registers) */
+    float (*ovf)[CON_FIELDS]; /* only when the pool is exhausted (rare): caller-provided array of MAXC - CON_FAST records, field
+                                 stride 1 (a pointer, so that the scalar members of this struct stay in registers) */
     int nc, overflow;
+    int head, tail, n_ovf; /* the env's contacts form a linked list in arbiter order: refs >= 0 are pool slots, < 0 overflow records */
     uint64_t touched;
 #ifdef MSOC_TIMING
     long long tm[8];
@@ -690,11 +693,34 @@ struct Work {
 #else
 #define MSOC_TICK(W, i, t) do { } while (0)
 #endif
-/* base pointer and field stride of contact k */
-MSOC_HD float *contact_ptr(Work &W, int k, int &fs)
+/* base pointer and field stride of the contact with reference p */
+constexpr int NIL = 0x7fffffff;
+MSOC_HD float *contact_ptr(const Work &W, int p, int &fs)
 {
-    if (k < CON_FAST) { fs = CON_FS; return W.con + k * SCR; }
-    fs = 1; return &W.ovf[k - CON_FAST][0];
+    if (p >= 0) { fs = CON_FS; return W.pool + p; }
+    fs = 1; return &W.ovf[-1 - p][0];
+}
+/* a new record at the end of the env's list; NIL if the env already has MAXC contacts */
+MSOC_HD int contact_alloc(Work &W)
+{
+    if (W.nc >= MAXC) { W.overflow++; return NIL; }
+    int p;
+#if defined(__CUDA_ARCH__)
+    const int s_ = atomicAdd(W.pool_count, 1);
+#else
+    const int s_ = (*W.pool_count)++;
+#endif
+    if (s_ < CON_FS) p = s_;
+    else {
+        if (W.n_ovf >= MAXC - CON_FAST) { W.overflow++; return NIL; }
+        p = -1 - W.n_ovf++;
+    }
+    int fs; float *cp = contact_ptr(W, p, fs);
+    cp[CF_NEXT * fs] = u2f((uint32_t)NIL);
+    if (W.nc == 0) W.head = p;
+    else { int fs2; float *tp = contact_ptr(W, W.tail, fs2); tp[CF_NEXT * fs2] = u2f((uint32_t)p); }
+    W.tail = p; W.nc++;
+    return p;
 }
 
 struct CacheIO {
@@ -746,8 +772,8 @@ MSOC_HD void add_contacts(Work &W, const CacheIO &cio, int pair, int a, int b, f
         if (m.count > 1 && key == m.key[1]) { cjn[1] = ojn; cjt[1] = ojt; }
     }
     for (int i = 0; i < m.count; i++) {
-        if (W.nc >= MAXC) { W.overflow++; continue; }
-        const int k = W.nc++;
+        const int k = contact_alloc(W);
+        if (k == NIL) continue;
         const V2 p1 = (i == 0) ? m.p1[0] : m.p1[1], p2 = (i == 0) ? m.p2[0] : m.p2[1];
         const int key = (i == 0) ? m.key[0] : m.key[1];
         /* stored so that body b is dynamic: a contact (a dynamic, b static) is kept as (static, a) with the
@@ -1258,7 +1284,7 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
     MSOC_TICK(W, 0, tk); /* prologue .. velocity update */
     if (run_contacts) {
         CacheIO cio;
-        W.nc = 0; W.overflow = 0; W.touched = 0ull;
+        W.nc = 0; W.overflow = 0; W.touched = 0ull; W.head = NIL; W.tail = NIL; W.n_ovf = 0;
         cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
         cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
         cio.n = A.n; cio.e = e; cio.old_count = old_count;
@@ -1314,12 +1340,12 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         MSOC_TICK(W, 1, tk); /* narrow phase + add_contacts */
 
         if (W.nc > 0) {
-            const int nfast = W.nc < CON_FAST ? W.nc : CON_FAST;
             /* ---- cpArbiterPreStep with the (parked) velocities from BEFORE the velocity update */
 #pragma unroll 1
-            for (int k = 0; k < nfast; k++) prestep_contact<CON_FS>(W.con + k * SCR, W.body, c);
-#pragma unroll 1
-            for (int k = CON_FAST; k < W.nc; k++) prestep_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
+            for (int p = W.head; p != NIL;) {
+                if (p >= 0) { float *cp = W.pool + p; prestep_contact<CON_FS>(cp, W.body, c); p = (int)f2u(cp[CF_NEXT * CON_FS]); }
+                else { float *cp = &W.ovf[-1 - p][0]; prestep_contact<1>(cp, W.body, c); p = (int)f2u(cp[CF_NEXT]); }
+            }
 #pragma unroll
             for (int i = 0; i < 5; i++) {
                 float *pb = W.body + i * SCR;
@@ -1328,9 +1354,10 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             }
             /* ---- cpArbiterApplyCachedImpulse */
 #pragma unroll 1
-            for (int k = 0; k < nfast; k++) warmstart_contact<CON_FS>(W.con + k * SCR, W.body, c);
-#pragma unroll 1
-            for (int k = CON_FAST; k < W.nc; k++) warmstart_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c);
+            for (int p = W.head; p != NIL;) {
+                if (p >= 0) { float *cp = W.pool + p; warmstart_contact<CON_FS>(cp, W.body, c); p = (int)f2u(cp[CF_NEXT * CON_FS]); }
+                else { float *cp = &W.ovf[-1 - p][0]; warmstart_contact<1>(cp, W.body, c); p = (int)f2u(cp[CF_NEXT]); }
+            }
             MSOC_TICK(W, 2, tk); /* prestep + warm start */
             /* ---- cpArbiterApplyImpulse x 10, contacts in arbiter order */
 #pragma unroll 1
@@ -1338,9 +1365,10 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             bc.vx = bc.vy = bc.w = bc.bx = bc.by = bc.bw = 0.0f;
             for (int it = 0; it < SOLVER_ITERS; it++) {
 #pragma unroll 1
-                for (int k = 0; k < nfast; k++) solve_contact<CON_FS>(W.con + k * SCR, W.body, c, bc);
-#pragma unroll 1
-                for (int k = CON_FAST; k < W.nc; k++) solve_contact<1>(&W.ovf[k - CON_FAST][0], W.body, c, bc);
+                for (int p = W.head; p != NIL;) {
+                    if (p >= 0) { float *cp = W.pool + p; const int nx_ = (int)f2u(cp[CF_NEXT * CON_FS]); solve_contact<CON_FS>(cp, W.body, c, bc); p = nx_; }
+                    else { float *cp = &W.ovf[-1 - p][0]; const int nx_ = (int)f2u(cp[CF_NEXT]); solve_contact<1>(cp, W.body, c, bc); p = nx_; }
+                }
             }
             bc_flush(bc, W.body);
 #pragma unroll
@@ -1356,9 +1384,10 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         MSOC_TICK(W, 3, tk); /* solver */
         /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
            arbiters younger than collision_persistence (3) */
-        for (int k = 0; k < W.nc && new_count < MAX_CACHE; k++) {
+        for (int p = W.head; p != NIL && new_count < MAX_CACHE;) {
             const int64_t o = (int64_t)new_count * A.n + e;
-            int fs; const float *cp = contact_ptr(W, k, fs);
+            int fs; const float *cp = contact_ptr(W, p, fs);
+            p = (int)f2u(cp[CF_NEXT * fs]);
             cio.new_info[o] = (f2u(cp[CF_META * fs]) >> 6) & 1023u; /* pair | key<<6, age 0 */
             cio.new_jn[o] = cp[CF_JN * fs]; cio.new_jt[o] = cp[CF_JT * fs];
             new_count++;

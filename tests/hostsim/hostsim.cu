@@ -130,13 +130,15 @@ void hsim_step(HostSim *h, const float *actions, const float *obs_in, float *obs
         float ovf_store[MAXC - CON_FAST][CON_FIELDS];
         Work W;
         W.ovf = ovf_store;
-        W.body = body; W.con = con; W.geom = geom; W.old = oldc;
+        int pool_count = 0;
+        W.body = body; W.pool = con; W.pool_count = &pool_count; W.geom = geom; W.old = oldc;
         const uint64_t gidx = h->global_offset + (uint64_t)e;
         if (!env_step(MODE_FAST, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, load)) {
             load_env(h->A, e, E);
             h->last_load[(size_t)e] = load;
             /* light class (one agent x wall pair): the register path; anything else: the general path */
             int dummy;
+            pool_count = 0;
             env_step(load == 0 ? MODE_LIGHT : MODE_FULL, E, actions + e * 12, h->cfg, h->A, h->cur, e, gidx, flags, W, out, dummy);
         }
         h->last_contacts[(size_t)e] = out.n_contacts;
