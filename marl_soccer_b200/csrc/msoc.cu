@@ -333,7 +333,13 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_LIGHT_MIN_BLOCKS) msoc_step_l
    the parked poses and the preloaded arbiter cache entries; afterwards the lanes' four new observation
    frames (lane-major, stride ENV_STRIDE). */
 static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
-constexpr size_t STEP_SMEM_BYTES = (size_t)STEP_BLOCK * ENV_STRIDE * sizeof(float);
+#ifndef MSOC_HEAVY_BLOCK
+#define MSOC_HEAVY_BLOCK 64 /* threads per block of the heavy contact kernel: one warp, so that an SM's registers and shared
+                               memory are handed to the light kernel warp by warp as the heavy batches finish */
+#endif
+constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
+constexpr int HEAVY_MIN_BLOCKS = STEP_MIN_BLOCKS * STEP_BLOCK / HEAVY_BLOCK; /* the same number of resident warps */
+constexpr size_t STEP_SMEM_BYTES = (size_t)HEAVY_BLOCK * ENV_STRIDE * sizeof(float);
 
 #ifdef MSOC_WARP_TIMING
 __device__ long long g_wb[8192 * 4];
@@ -342,10 +348,10 @@ extern "C" int msoc_debug_wb(long long *out) { return (int)cudaMemcpyFromSymbol(
 #ifndef MSOC_MERGE_LIGHT
 #define MSOC_MERGE_LIGHT 0 /* 1: the contact kernel also takes the light batches once the heavy ones are handed out */
 #endif
-__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
+__global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
-    __shared__ int s_pool_count[WARPS_PER_BLOCK];
+    __shared__ int s_pool_count[HEAVY_BLOCK / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
     const int n_light = MSOC_MERGE_LIGHT ? P.ctl[CTL_LIGHT] : 0, n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
@@ -614,7 +620,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
         ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, STEP_BLOCK, FAST_SMEM_BYTES);
     if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, STEP_BLOCK, STEP_SMEM_BYTES);
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);
     if (const char *ov = getenv("MSOC_BLOCKS_PER_SM")) { /* tuning experiments only */
         const int v = atoi(ov);
         if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v;
@@ -686,11 +692,12 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
        handle's own stream and fills the SMs as the heavy blocks drain.  The caller's stream then waits for it. */
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
-    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    const int64_t heavy_blocks_max = (h->n + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
+    const unsigned grid = (unsigned)(heavy_blocks_max < resident ? heavy_blocks_max : resident);
 #if !MSOC_MERGE_LIGHT
     CUDA_TRY(cudaEventRecord(h->ev_listed, st));
 #endif
-    msoc_step_contact_kernel<<<grid, STEP_BLOCK, STEP_SMEM_BYTES, st>>>(P);
+    msoc_step_contact_kernel<<<grid, HEAVY_BLOCK, STEP_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
 #if !MSOC_MERGE_LIGHT
