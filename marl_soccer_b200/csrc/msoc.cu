@@ -284,16 +284,19 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
 /* Light envs (exactly one agent x wall candidate pair, ~82 % of the contact envs): thread t of a batch steps
    one listed env with the register-only single-body solver of step_core.cuh (MODE_LIGHT).  Like the fast
    kernel it needs no solver scratch: shared memory only stages the frames. */
-#ifndef MSOC_LIGHT_MIN_BLOCKS
-#define MSOC_LIGHT_MIN_BLOCKS 4
+#ifndef MSOC_LIGHT_BLOCK
+#define MSOC_LIGHT_BLOCK 64 /* small blocks: they slip into an SM as soon as one heavy block has left it */
 #endif
-__global__ void __launch_bounds__(STEP_BLOCK, MSOC_LIGHT_MIN_BLOCKS) msoc_step_light_kernel(const __grid_constant__ StepParams P)
+constexpr int LIGHT_BLOCK = MSOC_LIGHT_BLOCK;
+constexpr int LIGHT_MIN_BLOCKS = 512 / LIGHT_BLOCK; /* 128 registers per thread */
+constexpr size_t LIGHT_SMEM_BYTES = (size_t)LIGHT_BLOCK * FAST_STRIDE * sizeof(float);
+__global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
     const int n_light = P.ctl[CTL_LIGHT]; /* final: the fast kernel has finished */
-    const int batches = (n_light + STEP_BLOCK - 1) / STEP_BLOCK;
+    const int batches = (n_light + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
     Work W; /* never touched in light mode */
     W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, MSOC_LIGHT_MIN_BLOCKS) msoc_step_l
         const int b = s_batch;
         __syncthreads();
         if (b >= batches) break;
-        const int idx = b * STEP_BLOCK + tid;
+        const int idx = b * LIGHT_BLOCK + tid;
         const bool have = idx < n_light;
         const int64_t my_env = have ? (int64_t)P.list[idx] : 0;
         bool fresh = false, ok = false;
@@ -615,9 +618,9 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
     if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute(msoc_step_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
+        ce = cudaFuncSetAttribute(msoc_step_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
     if (ce == cudaSuccess)
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, STEP_BLOCK, FAST_SMEM_BYTES);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, LIGHT_BLOCK, LIGHT_SMEM_BYTES);
     if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);
@@ -703,7 +706,8 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
 #if !MSOC_MERGE_LIGHT
     CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_listed, 0));
     const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
-    msoc_step_light_kernel<<<(unsigned)(n_tiles < light_resident ? n_tiles : light_resident), STEP_BLOCK, FAST_SMEM_BYTES, h->aux_stream>>>(P);
+    const int64_t light_blocks_max = (h->n + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
+    msoc_step_light_kernel<<<(unsigned)(light_blocks_max < light_resident ? light_blocks_max : light_resident), LIGHT_BLOCK, LIGHT_SMEM_BYTES, h->aux_stream>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev_light, h->aux_stream));
