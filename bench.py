@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/sec of the fused soccer step kernel on N B200s (weak scaling, envs sharded by
-global env index, no per-step collective), with the HBM roofline of the kernel, the end-to-end number
+"""bench.py -- env-steps/sec of the fused soccer step on N B200s (weak scaling, envs sharded by
+global env index, no per-step collective), with the HBM roofline of the step, the end-to-end number
 through the host-buffer C-ABI call, and the CPU oracle timed on the host cores as the reported baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl reference]
 
-One "step" = one launch of msoc_step_kernel over this rank's shard = E env-steps.  Under torchrun
-(N > 1) every rank owns E envs with global indices [rank*E, (rank+1)*E).
+One "step" = one msoc_step call over this rank's shard = E env-steps = three kernel launches (the streaming
+contact-free kernel over all envs, then the light and the heavy contact kernels side by side on two
+streams).  Under torchrun (N > 1) every rank owns E envs with global indices [rank*E, (rank+1)*E).
 """
 from __future__ import annotations
 
@@ -40,7 +41,7 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """dram bytes per env-step of msoc_step_kernel from the committed ncu --set full capture, or None."""
+    """dram bytes per step (sum over the three step kernels) from the committed ncu capture, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)
@@ -229,7 +230,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     stats = dict(zip([k for k, _ in _capi.MsocStats._fields_], stats_t.cpu().tolist()))
 
-    # kernel-only duration on this rank (the step is a single kernel; events bracket K back-to-back launches)
+    # device time of one step on this rank (three launches; events bracket K back-to-back steps)
     kernel_ms = e0.elapsed_time(e1) / args.steps
     value = world * n * args.steps / (elapsed_ms * 1e-3)
 
@@ -292,7 +293,9 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch_at_bench_size"),
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                     "kernel": "msoc_step_kernel", "kernel_ms": kernel_ms},
+                     "kernel": "msoc_step = msoc_step_fast_kernel + msoc_step_light_kernel || msoc_step_contact_kernel "
+                               "(whole step: algorithmic bytes of all envs / device time of the three launches)",
+                     "kernel_ms": kernel_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": args.e2e_steps, "api": "msoc_step_host (pinned host buffers)"},

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round measurement on a B200 box (run through gpurun): tests, full bench, reference arm, ncu launch list
-# and one ncu --set full capture of the step kernel.  Outputs land in gpurun_out/.
+# and one ncu --set full capture of one whole step (its three kernels).  Outputs land in gpurun_out/.
 set -u
 TAG=${1:-r01}
 mkdir -p gpurun_out
@@ -15,6 +15,6 @@ SHORT="python bench.py --steps 40 --warmup 5 --preroll 60 --e2e-steps 2 --no-cpu
 $SHORT > gpurun_out/${TAG}_short_plain.json 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $SHORT > gpurun_out/${TAG}_short_plain2.json 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:msoc_step -s 100 -c 2 -o gpurun_out/${TAG}_step_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:msoc_step -s 300 -c 3 -o gpurun_out/${TAG}_step_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log
 ls -la gpurun_out | tail -15

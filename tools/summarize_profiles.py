@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turns the raw outputs of tools/gpu_measure.sh (gpurun_out/<tag>_*) into the committed summaries under
-profiles/: bench lines, ncu launch list, the key metrics of the ncu --set full capture of msoc_step_kernel
+profiles/: bench lines, ncu launch list, the key metrics of the ncu --set full capture of one step (its three kernels)
 and profiles/traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic)."""
 import csv
 import json
@@ -40,24 +40,27 @@ KEYS = [
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
 ]
 launches = []
+names = []
 for r in rows[2:]:
     launches.append({k: (rows[1][h.index(k)], r[h.index(k)]) for k in KEYS if k in h})
+    names.append(r[h.index("Kernel Name")] if "Kernel Name" in h else "?")
 with open(os.path.join(P, f"{tag}_step_kernel_ncu_full.txt"), "w") as f:
     f.write(f"ncu --set full --clock-control none --import-source on -k regex:msoc_step (tools/gpu_measure.sh {tag}); "
             "same command exited 0 without ncu first.  Cold-cache, serialised replays: use shares, not absolutes.\n")
     short = json.loads(open(os.path.join(G, f"{tag}_short_plain.json")).read().strip().splitlines()[-1])
     f.write(f"workload: {short['config']['envs_per_gpu']} envs per launch ({short['config']['workload']})\n\n")
     for i, L in enumerate(launches):
-        f.write(f"--- launch {i}\n")
+        f.write(f"--- launch {i}: {names[i]}\n")
         for k, (u, v) in L.items():
             f.write(f"{k:90s} {v} {u}\n")
 def to_bytes(unit, v):
     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     return float(v) * m[unit]
-L = launches[-1]
-rd = to_bytes(*L["dram__bytes_read.sum"]); wr = to_bytes(*L["dram__bytes_write.sum"])
+# one step = the three captured launches (fast, heavy contact, light): DRAM traffic of the step = their sum
+rd = sum(to_bytes(*L["dram__bytes_read.sum"]) for L in launches)
+wr = sum(to_bytes(*L["dram__bytes_write.sum"]) for L in launches)
 n = short["config"]["envs_per_gpu"]
-traffic = {"tag": tag, "kernel": "msoc_step_kernel", "envs_per_launch": n, "dram_bytes_read": rd, "dram_bytes_write": wr,
+traffic = {"tag": tag, "kernel": "msoc_step (" + " + ".join(names) + ")", "envs_per_launch": n, "dram_bytes_read": rd, "dram_bytes_write": wr,
            "dram_bytes_per_launch_at_bench_size": rd + wr, "dram_bytes_per_env_step": (rd + wr) / n,
            "algorithmic_bytes_per_env_step": 2194, "source": f"profiles/{tag}_step_kernel_ncu_full.txt"}
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
