@@ -1,0 +1,112 @@
+"""Device-resident rollout half of the reference's PPO trainer (marl_soccer_b200/rollout.py):
+network / normaliser / GAE arithmetic against plain restatements of marl-soccer.ipynb on the CPU, and the
+in-loop rollout on the simulator on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from marl_soccer_b200.rollout import Agent, RolloutBuffer, RunningMeanStd, collect_rollout, compute_gae
+
+
+def test_agent_architecture_matches_reference_checkpoint_layout():
+    """marl-soccer.ipynb:125-190: 66 -> 512 -> 256 -> 128 -> 64 -> (3 | 1), tanh, state-independent log-std; the
+    parameter names are the reference's, so its `.ppo_model` state dicts load unchanged."""
+    a = Agent()
+    sd = a.state_dict()
+    assert sd["actor_logstd"].shape == (1, 3)
+    for net, out in (("critic", 1), ("actor_mean", 3)):
+        dims = [(512, 66), (256, 512), (128, 256), (64, 128), (out, 64)]
+        for k, d in zip((0, 2, 4, 6, 8), dims):
+            assert tuple(sd[f"{net}.{k}.weight"].shape) == d
+            assert tuple(sd[f"{net}.{k}.bias"].shape) == (d[0],)
+    x = torch.randn(7, 66)
+    act, logp, ent, val = a.get_action_and_value(x)
+    assert act.shape == (7, 3) and logp.shape == (7,) and ent.shape == (7,) and val.shape == (7, 1)
+    # the log-prob of a given action is the diagonal Gaussian's
+    mean = a.actor_mean(x)
+    ref = torch.distributions.Normal(mean, torch.ones_like(mean)).log_prob(act).sum(1)
+    _, logp2, _, _ = a.get_action_and_value(x, act)
+    assert torch.allclose(logp2, ref, atol=1e-6)
+
+
+def test_running_mean_std_matches_batch_statistics():
+    """marl-soccer.ipynb:264-296: parallel-variance update; after all batches mean/var equal those of the
+    concatenated stream (up to the unit prior count the reference does not use: count starts at 0 here)."""
+    rng = np.random.default_rng(0)
+    chunks = [rng.normal(3.0, 2.0, (n, 66)) for n in (100, 1, 57, 300)]
+    rms = RunningMeanStd((66,), "cpu")
+    for c in chunks:
+        rms.update(torch.as_tensor(c))
+    allx = np.concatenate(chunks)
+    assert np.allclose(rms.mean.numpy(), allx.mean(0), atol=1e-10)
+    assert np.allclose(rms.var.numpy(), allx.var(0), atol=1e-10)
+    x = torch.as_tensor(allx[:5], dtype=torch.float32)
+    z = rms.normalize(x)
+    ref = np.clip((allx[:5] - allx.mean(0)) / (allx.std(0) + 1e-8), -10, 10)
+    assert np.allclose(z.numpy(), ref, atol=1e-4)
+
+
+def test_gae_matches_the_reference_recursion():
+    """marl-soccer.ipynb:454-464, restated with plain Python loops."""
+    T, n = 9, 5
+    g = torch.Generator().manual_seed(1)
+    buf = RolloutBuffer(T, n, "cpu")
+    buf.rewards = torch.randn((T, n, 2), generator=g)
+    buf.values = torch.randn((T, n, 2), generator=g)
+    buf.dones = (torch.rand((T, n, 2), generator=g) < 0.2).float()
+    next_done = (torch.rand((n, 2), generator=g) < 0.5).float()
+
+    class ConstCritic(Agent):
+        def get_value(self, x):
+            return torch.full((x.shape[0], 1), 0.25)
+    agent = ConstCritic()
+    rms = RunningMeanStd((66,), "cpu")
+    next_obs = torch.zeros((n, 2, 66))
+    adv, ret = compute_gae(agent, rms, buf, next_obs, next_done, gamma=0.9, gae_lambda=0.8)
+    exp = np.zeros((T, n, 2))
+    last = np.zeros((n, 2))
+    for t in reversed(range(T)):
+        if t == T - 1:
+            nonterm, nv = 1.0 - next_done.numpy(), np.full((n, 2), 0.25)
+        else:
+            nonterm, nv = 1.0 - buf.dones[t + 1].numpy(), buf.values[t + 1].numpy()
+        delta = buf.rewards[t].numpy() + 0.9 * nv * nonterm - buf.values[t].numpy()
+        last = delta + 0.9 * 0.8 * nonterm * last
+        exp[t] = last
+    assert np.allclose(adv.numpy(), exp, atol=1e-5)
+    assert np.allclose(ret.numpy(), exp + buf.values.numpy(), atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_rollout_loop_on_the_device():
+    """128 steps of 4 096 envs with the policy in the loop: everything stays on the GPU, the buffers hold what
+    the simulator returned, red actions are uniform in [-1, 1], env-steps and episode statistics add up."""
+    import parity_util as P
+    from marl_soccer_b200.sim import BatchedSoccerSim
+    dev = torch.device("cuda:0")
+    n, T = 4096, 128
+    cfg = dict(P.CONFIG)
+    cfg["simulation"] = {"max_steps": 50}
+    sim = BatchedSoccerSim(n, config=cfg, device=dev, seed=3)
+    torch.manual_seed(0)
+    agent = Agent().to(dev)
+    rms = RunningMeanStd((66,), dev)
+    buf = RolloutBuffer(T, n, dev)
+    obs = sim.reset(2, seed=5)[:, :2].clone()
+    done = torch.zeros((n, 2), device=dev)
+    sim.stats(reset=True)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    next_obs, next_done = collect_rollout(sim, agent, rms, buf, obs, done, generator=gen)
+    st = sim.stats()
+    assert st["env_steps"] == n * T
+    assert st["episodes"] == n * (T // 50)          # truncation at max_steps, auto-reset in the step kernel
+    assert torch.equal(buf.obs[0], obs)
+    assert float(buf.dones.sum()) == 2 * (st["episodes"] - n * (1 if T % 50 == 0 else 0))
+    assert torch.isfinite(buf.rewards).all() and torch.isfinite(buf.values).all() and torch.isfinite(buf.logprobs).all()
+    assert next_obs.shape == (n, 2, 66) and next_done.shape == (n, 2)
+    assert rms.count == n * T * 2
+    # red agents: uniform random actions (marl-soccer.ipynb:397-400)
+    red = sim.actions[:, 2:]
+    assert float(red.min()) >= -1.0 and float(red.max()) <= 1.0 and abs(float(red.mean())) < 0.02
+    adv, ret = compute_gae(agent, rms, buf, next_obs, next_done)
+    assert adv.shape == (T, n, 2) and torch.isfinite(adv).all() and torch.isfinite(ret).all()
