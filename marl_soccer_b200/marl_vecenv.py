@@ -3,7 +3,7 @@
 `SyncMultiAgentVecEnv(env_fns)` keeps the NumPy contract of the reference -- reset() -> (N,4,66) float32;
 step((N,4,3)) -> obs (N,4,66) float32, rewards (N,4) float64 (columns 2,3 are zero), terminations (N,4)
 bool (all False), truncations (N,4) bool, infos = sequence of N dicts keyed by agent -- but the Python
-`for env in self.envs` loop (marl_vecenv.py:39) is one launch of the fused CUDA step kernel over all N
+`for env in self.envs` loop (marl_vecenv.py:39) is one fused CUDA step (three kernel launches) over all N
 envs, including the auto-reset in full-random mode (marl_vecenv.py:45-53).
 
 `TorchSoccerVecEnv` is the zero-copy variant for device-resident trainers: same semantics, torch CUDA

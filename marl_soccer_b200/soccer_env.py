@@ -3,7 +3,7 @@ factories `soccer_raw_env` / `soccerenv` / `make_env` and `get_observation_scale
 spaces, dict packaging, option keys and exceptions (soccer_simulation/soccer_env.py:16-221).
 
 The embedded `Game` of the reference (soccer_env.py:59) is replaced by a one-env handle of the CUDA
-simulator (include/msoc.h); `SoccerEnv.step` is one launch of the fused step kernel.  There is no
+simulator (include/msoc.h); `SoccerEnv.step` is one fused device step (three kernel launches).  There is no
 CPU physics path: constructing a SoccerEnv needs the built extension and a CUDA device.
 """
 from __future__ import annotations
