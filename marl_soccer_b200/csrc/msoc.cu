@@ -117,11 +117,7 @@ __device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, 
             const int64_t ew = __shfl_sync(0xffffffffu, my_env, l0 + w);
             const float2 *pi = in2 + ew * 132 + lane + 11;
             po[w] = out2 + ew * 132 + lane;
-#ifdef MSOC_EXP_NOHIST /* timing experiment only: no history loads (wrong observations) */
-            const bool ld = false;
-#else
             const bool ld = ((mb >> w) & 1u) && lane_hist && !((fresh >> (l0 + w)) & 1u);
-#endif
 #pragma unroll
             for (int a = 0; a < 4; a++) {
                 const float *sp = s_lane + (l0 + w) * ENV_STRIDE + a * 22;
@@ -344,21 +340,14 @@ constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
 constexpr int HEAVY_MIN_BLOCKS = STEP_MIN_BLOCKS * STEP_BLOCK / HEAVY_BLOCK; /* the same number of resident warps */
 constexpr size_t STEP_SMEM_BYTES = (size_t)HEAVY_BLOCK * ENV_STRIDE * sizeof(float);
 
-#ifdef MSOC_WARP_TIMING
-__device__ long long g_wb[8192 * 4];
-extern "C" int msoc_debug_wb(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_wb, sizeof g_wb); }
-#endif
-#ifndef MSOC_MERGE_LIGHT
-#define MSOC_MERGE_LIGHT 0 /* 1: the contact kernel also takes the light batches once the heavy ones are handed out */
-#endif
 __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
     __shared__ int s_pool_count[HEAVY_BLOCK / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
-    const int n_light = MSOC_MERGE_LIGHT ? P.ctl[CTL_LIGHT] : 0, n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
-    const int heavy_batches = (n_heavy + 31) / 32, light_batches = (n_light + 31) / 32;
+    const int n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
+    const int heavy_batches = (n_heavy + 31) / 32;
     const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
     float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
 
@@ -371,38 +360,25 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
     W.pool_count = &s_pool_count[warp];
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
     W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
-    bool heavy = true; /* warp-uniform: still taking heavy batches */
 #pragma unroll 1
     while (true) {
-        /* every WARP takes its own batches of 32 envs (the scratch is per warp, so the warps of a block never wait
-           for each other): the heavy ones first -- the batches differ a lot in length --, handed out dynamically */
+        /* every WARP takes its own batches of 32 envs, handed out dynamically (the scratch is per warp, so the warps
+           of a block never wait for each other; the batches differ a lot in length) */
         int b = 0;
-        if (heavy) {
-            if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_HEAVY, 1);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= heavy_batches) heavy = false;
-        }
-        if (!heavy) {
-            if (light_batches == 0) break;
-            if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= light_batches) break;
-        }
+        if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_HEAVY, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= heavy_batches) break;
         const int idx = b * 32 + lane;
-        const bool have = idx < (heavy ? n_heavy : n_light);
+        const bool have = idx < n_heavy;
         int64_t my_env = 0;
-        if (have) my_env = (int64_t)(heavy ? P.list[P.A.n - 1 - idx] : P.list[idx]);
-#ifdef MSOC_WARP_TIMING
-        const long long wt0 = clock64(); const int c0 = T.contacts;
-#endif
+        if (have) my_env = (int64_t)P.list[P.A.n - 1 - idx];
         bool fresh = false, ok = false;
         int load = 0;
         if (lane == 0) *W.pool_count = 0; /* the warp's contact pool is empty */
         __syncwarp();
         {
             Env E;
-            if (have) ok = heavy ? step_one_env(MODE_FULL, P, my_env, E, W, load, fresh, T)
-                                 : step_one_env(MODE_LIGHT, P, my_env, E, W, load, fresh, T);
+            if (have) ok = step_one_env(MODE_FULL, P, my_env, E, W, load, fresh, T);
             __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
             if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
         }
@@ -411,13 +387,6 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         __syncwarp();
         if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
         __syncwarp();
-#ifdef MSOC_WARP_TIMING
-        {
-            int nc = T.contacts - c0, mx = nc, sum = nc;
-            for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-            if (lane == 0 && heavy && b < 8192) { g_wb[b * 4] = clock64() - wt0; g_wb[b * 4 + 1] = mx; g_wb[b * 4 + 2] = sum; g_wb[b * 4 + 3] = (long long)blockIdx.x; }
-        }
-#endif
     }
     flush_tally(T, P.stats, lane);
 }
@@ -624,10 +593,6 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);
-    if (const char *ov = getenv("MSOC_BLOCKS_PER_SM")) { /* tuning experiments only */
-        const int v = atoi(ov);
-        if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v;
-    }
     if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) {
         cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
     }
@@ -697,13 +662,10 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
     const int64_t heavy_blocks_max = (h->n + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
     const unsigned grid = (unsigned)(heavy_blocks_max < resident ? heavy_blocks_max : resident);
-#if !MSOC_MERGE_LIGHT
     CUDA_TRY(cudaEventRecord(h->ev_listed, st));
-#endif
     msoc_step_contact_kernel<<<grid, HEAVY_BLOCK, STEP_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-#if !MSOC_MERGE_LIGHT
     CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_listed, 0));
     const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
     const int64_t light_blocks_max = (h->n + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
@@ -712,7 +674,6 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev_light, h->aux_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_light, 0));
-#endif
     h->cur ^= 1;
     CUDA_TRY(cudaGetLastError());
     return MSOC_OK;

@@ -679,20 +679,7 @@ struct Work {
     int nc, overflow;
     int head, tail, n_ovf; /* the env's contacts form a linked list in arbiter order: refs >= 0 are pool slots, < 0 overflow records */
     uint64_t touched;
-#ifdef MSOC_TIMING
-    long long tm[8];
-#endif
 };
-#ifdef MSOC_TIMING
-#if defined(__CUDA_ARCH__)
-#define MSOC_CLOCK() clock64()
-#else
-#define MSOC_CLOCK() 0ll
-#endif
-#define MSOC_TICK(W, i, t) do { const long long _n = MSOC_CLOCK(); (W).tm[i] += _n - (t); (t) = _n; } while (0)
-#else
-#define MSOC_TICK(W, i, t) do { } while (0)
-#endif
 /* base pointer and field stride of the contact with reference p */
 constexpr int NIL = 0x7fffffff;
 MSOC_HD float *contact_ptr(const Work &W, int p, int &fs)
@@ -971,9 +958,6 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
                       uint64_t gidx, uint32_t step_flags, Work &W, StepOut &out, int &load)
 {
     const bool FAST = MODE == MODE_FAST, LIGHT = MODE == MODE_LIGHT;
-#ifdef MSOC_TIMING
-    long long tk = MSOC_CLOCK();
-#endif
     /* ---- soccer_env.py:118-125: clip to [-1, 1], scale in float32 */
     float Fx[4], Fy[4], Tq[4];
     float cs[4], sn[4];
@@ -1281,7 +1265,6 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         }
     }
 
-    MSOC_TICK(W, 0, tk); /* prologue .. velocity update */
     if (run_contacts) {
         CacheIO cio;
         W.nc = 0; W.overflow = 0; W.touched = 0ull; W.head = NIL; W.tail = NIL; W.n_ovf = 0;
@@ -1337,7 +1320,6 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             }
         }
         n_contacts = W.nc; overflow = W.overflow;
-        MSOC_TICK(W, 1, tk); /* narrow phase + add_contacts */
 
         if (W.nc > 0) {
             /* ---- cpArbiterPreStep with the (parked) velocities from BEFORE the velocity update */
@@ -1358,11 +1340,12 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
                 if (p >= 0) { float *cp = W.pool + p; warmstart_contact<CON_FS>(cp, W.body, c); p = (int)f2u(cp[CF_NEXT * CON_FS]); }
                 else { float *cp = &W.ovf[-1 - p][0]; warmstart_contact<1>(cp, W.body, c); p = (int)f2u(cp[CF_NEXT]); }
             }
-            MSOC_TICK(W, 2, tk); /* prestep + warm start */
             /* ---- cpArbiterApplyImpulse x 10, contacts in arbiter order */
-#pragma unroll 1
             BodyCache bc; bc.cur = -1;
             bc.vx = bc.vy = bc.w = bc.bx = bc.by = bc.bw = 0.0f;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
             for (int it = 0; it < SOLVER_ITERS; it++) {
 #pragma unroll 1
                 for (int p = W.head; p != NIL;) {
@@ -1381,7 +1364,6 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             for (int i = 0; i < 4; i++) E.wb[i] = W.body[i * SCR + BF_BW * BODY_FS];
         }
 
-        MSOC_TICK(W, 3, tk); /* solver */
         /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
            arbiters younger than collision_persistence (3) */
         for (int p = W.head; p != NIL && new_count < MAX_CACHE;) {
@@ -1408,7 +1390,6 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #pragma unroll
         for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
-    MSOC_TICK(W, 4, tk); /* cache write-out */
     E.flags = (E.flags & ~FLAG_CACHE_MASK) | (uint32_t)new_count;
 
     /* ---- goal test (game/game.py:401-412), strict inequalities */
