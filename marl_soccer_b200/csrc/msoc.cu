@@ -449,9 +449,8 @@ __global__ void msoc_get_state_kernel(Arrays A, int cur, const int64_t *idx, int
     const uint32_t cnt = E.flags & FLAG_CACHE_MASK;
     S.cache_count = cnt;
     for (uint32_t j = 0; j < cnt; j++) {
-        S.cache_info[j] = A.cache_info[cur][(int64_t)j * A.n + e];
-        S.cache_jn[j] = A.cache_jn[cur][(int64_t)j * A.n + e];
-        S.cache_jt[j] = A.cache_jt[cur][(int64_t)j * A.n + e];
+        const uint32_t *c = A.cache[cur] + cache_slot(e, (int)j);
+        S.cache_info[j] = c[0]; S.cache_jn[j] = __uint_as_float(c[1]); S.cache_jt[j] = __uint_as_float(c[2]);
     }
     out[t] = S;
 }
@@ -473,9 +472,8 @@ __global__ void msoc_set_state_kernel(Arrays A, int cur, const int64_t *idx, int
     E.flags = cnt | (((uint32_t)S.mode & 3u) << FLAG_MODE_SHIFT);
     A.spawn_count[e] = S.spawn_count; A.seed[e] = S.seed;
     for (uint32_t j = 0; j < cnt; j++) {
-        A.cache_info[cur][(int64_t)j * A.n + e] = S.cache_info[j];
-        A.cache_jn[cur][(int64_t)j * A.n + e] = S.cache_jn[j];
-        A.cache_jt[cur][(int64_t)j * A.n + e] = S.cache_jt[j];
+        uint32_t *c = A.cache[cur] + cache_slot(e, (int)j);
+        c[0] = S.cache_info[j]; c[1] = __float_as_uint(S.cache_jn[j]); c[2] = __float_as_uint(S.cache_jt[j]);
     }
     store_env(A, e, E);
 }
@@ -544,12 +542,8 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     const size_t o_vb01 = take(n * sizeof(float4)), o_vb23 = take(n * sizeof(float4)), o_vb4w = take(n * sizeof(float4));
     const size_t o_wb23 = take(n * sizeof(float2));
     const size_t o_seed = take(n * sizeof(uint64_t)), o_sc = take(n * sizeof(uint32_t));
-    size_t o_ci[2], o_cjn[2], o_cjt[2];
-    for (int k = 0; k < 2; k++) {
-        o_ci[k] = take(n * MAX_CACHE * sizeof(uint32_t));
-        o_cjn[k] = take(n * MAX_CACHE * sizeof(float));
-        o_cjt[k] = take(n * MAX_CACHE * sizeof(float));
-    }
+    size_t o_cache[2];
+    for (int k = 0; k < 2; k++) o_cache[k] = take(n * MAX_CACHE * 3 * sizeof(uint32_t));
     const size_t o_obs = take(n * 4 * OBS * sizeof(float)), o_act = take(n * 12 * sizeof(float));
     const size_t o_rew = take(n * 2 * sizeof(float)), o_done = take(n), o_goal = take(n), o_mask = take(n);
     const size_t o_score = take(n * 2 * sizeof(int32_t));
@@ -572,9 +566,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     A.wb23 = (float2 *)(base + o_wb23);
     A.seed = (uint64_t *)(base + o_seed); A.spawn_count = (uint32_t *)(base + o_sc);
     for (int k = 0; k < 2; k++) {
-        A.cache_info[k] = (uint32_t *)(base + o_ci[k]);
-        A.cache_jn[k] = (float *)(base + o_cjn[k]);
-        A.cache_jt[k] = (float *)(base + o_cjt[k]);
+        A.cache[k] = (uint32_t *)(base + o_cache[k]);
     }
     h->d_obs = (float *)(base + o_obs); h->d_act = (float *)(base + o_act); h->d_rew = (float *)(base + o_rew);
     h->d_done = (uint8_t *)(base + o_done); h->d_goal = (int8_t *)(base + o_goal); h->d_mask = (uint8_t *)(base + o_mask);

@@ -93,8 +93,7 @@ struct Arrays {
     float2 *wb23;      /* w_bias agents 2-3 */
     uint64_t *seed;    /* per-env Philox key */
     uint32_t *spawn_count;
-    uint32_t *cache_info[2]; /* [MAX_CACHE][n], ping-pong */
-    float *cache_jn[2], *cache_jt[2];
+    uint32_t *cache[2]; /* arbiter cache, ping-pong between steps: entry j of env e = 3 words at cache_slot(e, j) */
 };
 
 struct Env {
@@ -105,6 +104,10 @@ struct Env {
     int32_t steps, score_b, score_r;
     uint32_t flags;
 };
+
+/* arbiter cache entry j of env e: (info, accumulated normal impulse, accumulated tangent impulse), the entries of an
+   env contiguous (a lane's few live entries share one or two sectors) */
+MSOC_HD int64_t cache_slot(int64_t e, int j) { return (e * MAX_CACHE + j) * 3; }
 
 /* ------------------------------------------------------------------------------------ small math */
 struct V2 { float x, y; };
@@ -711,8 +714,8 @@ MSOC_HD int contact_alloc(Work &W)
 }
 
 struct CacheIO {
-    const uint32_t *old_info; const float *old_jn, *old_jt; /* [MAX_CACHE][n] */
-    uint32_t *new_info; float *new_jn, *new_jt;
+    const uint32_t *oldc; /* previous step's entries of this env: 3 words each */
+    uint32_t *newc;       /* next step's */
     int64_t n, e;
     int old_count;
 };
@@ -721,15 +724,15 @@ struct CacheIO {
    batch of independent loads), the rare further ones from global memory */
 MSOC_HD uint32_t old_info_at(const Work &W, const CacheIO &cio, int j)
 {
-    return j < OLD_FAST ? f2u(W.old[j * SCR]) : cio.old_info[(int64_t)j * cio.n + cio.e];
+    return j < OLD_FAST ? f2u(W.old[j * SCR]) : cio.oldc[3 * j];
 }
 MSOC_HD float old_jn_at(const Work &W, const CacheIO &cio, int j)
 {
-    return j < OLD_FAST ? W.old[(OLD_FAST + j) * SCR] : cio.old_jn[(int64_t)j * cio.n + cio.e];
+    return j < OLD_FAST ? W.old[(OLD_FAST + j) * SCR] : u2f(cio.oldc[3 * j + 1]);
 }
 MSOC_HD float old_jt_at(const Work &W, const CacheIO &cio, int j)
 {
-    return j < OLD_FAST ? W.old[(2 * OLD_FAST + j) * SCR] : cio.old_jt[(int64_t)j * cio.n + cio.e];
+    return j < OLD_FAST ? W.old[(2 * OLD_FAST + j) * SCR] : u2f(cio.oldc[3 * j + 2]);
 }
 
 /* friction product of a pair id (cpArbiterUpdate u = ua*ub) */
@@ -1068,16 +1071,14 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
     if (!contact_path && old_count != 0) {
         /* nothing can touch this step, but the env still carries arbiters of contacts that ended
            less than collision_persistence (3) steps ago: age them (cpSpaceArbiterSetFilter) */
-        const uint32_t *oi_ = A.cache_info[cur]; const float *ojn = A.cache_jn[cur], *ojt = A.cache_jt[cur];
-        uint32_t *ni_ = A.cache_info[cur ^ 1]; float *njn = A.cache_jn[cur ^ 1], *njt = A.cache_jt[cur ^ 1];
+        const uint32_t *oc = A.cache[cur] + cache_slot(e, 0);
+        uint32_t *nc_ = A.cache[cur ^ 1] + cache_slot(e, 0);
         for (int j = 0; j < old_count; j++) {
-            const int64_t oi = (int64_t)j * A.n + e;
-            const uint32_t info = oi_[oi];
+            const uint32_t info = oc[3 * j];
             const uint32_t age = (info >> 10) & 3u;
             if (age >= 2u) continue;
-            const int64_t o = (int64_t)new_count * A.n + e;
-            ni_[o] = (info & 1023u) | ((age + 1u) << 10);
-            njn[o] = ojn[oi]; njt[o] = ojt[oi];
+            nc_[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
+            nc_[3 * new_count + 1] = oc[3 * j + 1]; nc_[3 * new_count + 2] = oc[3 * j + 2];
             new_count++;
         }
     }
@@ -1159,8 +1160,8 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         /* ---- light mode: exactly one candidate pair, agent l_i x static segment.  The same arithmetic as
            the general path below (narrow phase, arbiter cache, pre-step, warm start, 10 iterations, cache
            write-out) for a single dynamic body and at most two contacts, entirely in registers. */
-        const uint32_t *oi_ = A.cache_info[cur]; const float *ojn_ = A.cache_jn[cur], *ojt_ = A.cache_jt[cur];
-        uint32_t *ni_ = A.cache_info[cur ^ 1]; float *njn_ = A.cache_jn[cur ^ 1], *njt_ = A.cache_jt[cur ^ 1];
+        const uint32_t *oc = A.cache[cur] + cache_slot(e, 0);
+        uint32_t *nc_ = A.cache[cur ^ 1] + cache_slot(e, 0);
         Manifold m;
         const Seg g = get_segment(l_idx & 7);
         collide_segment_box(g, mk(sel4(E.px, l_i), sel4(E.py, l_i)), sel4(cs, l_i), sel4(sn, l_i), m);
@@ -1170,12 +1171,11 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             bool first = true;
             float jn0 = 0.0f, jt0 = 0.0f, jn1 = 0.0f, jt1 = 0.0f;
             for (int j = 0; j < old_count; j++) {
-                const int64_t oi = (int64_t)j * A.n + e;
-                const uint32_t info = oi_[oi];
+                const uint32_t info = oc[3 * j];
                 if ((int)(info & 63u) != l_idx) continue;
                 if (((info >> 10) & 3u) == 0u) first = false;
                 const int key = (int)((info >> 6) & 15u);
-                const float ojn = ojn_[oi], ojt = ojt_[oi];
+                const float ojn = u2f(oc[3 * j + 1]), ojt = u2f(oc[3 * j + 2]);
                 if (key == m.key[0]) { jn0 = ojn; jt0 = ojt; }
                 if (m.count > 1 && key == m.key[1]) { jn1 = ojn; jt1 = ojt; }
             }
@@ -1240,27 +1240,21 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             for (int k = 0; k < 4; k++)
                 if (k == l_i) { E.vx[k] = vx; E.vy[k] = vy; E.w[k] = w; E.vbx[k] = bx; E.vby[k] = by; E.wb[k] = bw; }
             /* this step's contacts open the arbiter cache of the next step (age 0) */
-            {
-                const int64_t o = e; /* slot 0 */
-                ni_[o] = (uint32_t)l_idx | ((uint32_t)m.key[0] << 6); njn_[o] = jn0; njt_[o] = jt0;
-                new_count = 1;
-            }
+            nc_[0] = (uint32_t)l_idx | ((uint32_t)m.key[0] << 6); nc_[1] = f2u(jn0); nc_[2] = f2u(jt0);
+            new_count = 1;
             if (two) {
-                const int64_t o = A.n + e; /* slot 1 */
-                ni_[o] = (uint32_t)l_idx | ((uint32_t)m.key[1] << 6); njn_[o] = jn1; njt_[o] = jt1;
+                nc_[3] = (uint32_t)l_idx | ((uint32_t)m.key[1] << 6); nc_[4] = f2u(jn1); nc_[5] = f2u(jt1);
                 new_count = 2;
             }
         }
         /* then the untouched arbiters younger than collision_persistence (3) */
         for (int j = 0; j < old_count; j++) {
-            const int64_t oi = (int64_t)j * A.n + e;
-            const uint32_t info = oi_[oi];
+            const uint32_t info = oc[3 * j];
             const uint32_t age = (info >> 10) & 3u;
             if ((m.count > 0 && (int)(info & 63u) == l_idx) || age >= 2u) continue;
             if (new_count >= MAX_CACHE) { overflow++; continue; }
-            const int64_t o = (int64_t)new_count * A.n + e;
-            ni_[o] = (info & 1023u) | ((age + 1u) << 10);
-            njn_[o] = ojn_[oi]; njt_[o] = ojt_[oi];
+            nc_[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
+            nc_[3 * new_count + 1] = oc[3 * j + 1]; nc_[3 * new_count + 2] = oc[3 * j + 2];
             new_count++;
         }
     }
@@ -1268,17 +1262,15 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
     if (run_contacts) {
         CacheIO cio;
         W.nc = 0; W.overflow = 0; W.touched = 0ull; W.head = NIL; W.tail = NIL; W.n_ovf = 0;
-        cio.old_info = A.cache_info[cur]; cio.old_jn = A.cache_jn[cur]; cio.old_jt = A.cache_jt[cur];
-        cio.new_info = A.cache_info[cur ^ 1]; cio.new_jn = A.cache_jn[cur ^ 1]; cio.new_jt = A.cache_jt[cur ^ 1];
+        cio.oldc = A.cache[cur] + cache_slot(e, 0); cio.newc = A.cache[cur ^ 1] + cache_slot(e, 0);
         cio.n = A.n; cio.e = e; cio.old_count = old_count;
         /* preload the cached arbiter entries: independent loads, one memory round trip */
 #pragma unroll
         for (int j = 0; j < OLD_FAST; j++) {
             if (j < old_count) {
-                const int64_t oi = (int64_t)j * A.n + e;
-                W.old[j * SCR] = u2f(cio.old_info[oi]);
-                W.old[(OLD_FAST + j) * SCR] = cio.old_jn[oi];
-                W.old[(2 * OLD_FAST + j) * SCR] = cio.old_jt[oi];
+                W.old[j * SCR] = u2f(cio.oldc[3 * j]);
+                W.old[(OLD_FAST + j) * SCR] = u2f(cio.oldc[3 * j + 1]);
+                W.old[(2 * OLD_FAST + j) * SCR] = u2f(cio.oldc[3 * j + 2]);
             }
         }
 
@@ -1367,11 +1359,10 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         /* ---- arbiter cache for the next step: this step's contacts (age 0), then the untouched
            arbiters younger than collision_persistence (3) */
         for (int p = W.head; p != NIL && new_count < MAX_CACHE;) {
-            const int64_t o = (int64_t)new_count * A.n + e;
             int fs; const float *cp = contact_ptr(W, p, fs);
             p = (int)f2u(cp[CF_NEXT * fs]);
-            cio.new_info[o] = (f2u(cp[CF_META * fs]) >> 6) & 1023u; /* pair | key<<6, age 0 */
-            cio.new_jn[o] = cp[CF_JN * fs]; cio.new_jt[o] = cp[CF_JT * fs];
+            cio.newc[3 * new_count] = (f2u(cp[CF_META * fs]) >> 6) & 1023u; /* pair | key<<6, age 0 */
+            cio.newc[3 * new_count + 1] = f2u(cp[CF_JN * fs]); cio.newc[3 * new_count + 2] = f2u(cp[CF_JT * fs]);
             new_count++;
         }
         for (int j = 0; j < old_count; j++) {
@@ -1379,9 +1370,8 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             const uint32_t age = (info >> 10) & 3u;
             if (((W.touched >> (info & 63u)) & 1ull) || age >= 2u) continue;
             if (new_count >= MAX_CACHE) { overflow++; continue; }
-            const int64_t o = (int64_t)new_count * A.n + e;
-            cio.new_info[o] = (info & 1023u) | ((age + 1u) << 10);
-            cio.new_jn[o] = old_jn_at(W, cio, j); cio.new_jt[o] = old_jt_at(W, cio, j);
+            cio.newc[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
+            cio.newc[3 * new_count + 1] = f2u(old_jn_at(W, cio, j)); cio.newc[3 * new_count + 2] = f2u(old_jt_at(W, cio, j));
             new_count++;
         }
         /* poses back from the scratch */

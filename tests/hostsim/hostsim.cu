@@ -70,9 +70,7 @@ HostSim *hsim_create(const msoc_config *cfg, int64_t n, uint64_t seed, uint64_t 
     A.wb23 = alloc<float2>(h, N);
     A.seed = alloc<uint64_t>(h, N); A.spawn_count = alloc<uint32_t>(h, N);
     for (int k = 0; k < 2; k++) {
-        A.cache_info[k] = alloc<uint32_t>(h, N * MAX_CACHE);
-        A.cache_jn[k] = alloc<float>(h, N * MAX_CACHE);
-        A.cache_jt[k] = alloc<float>(h, N * MAX_CACHE);
+        A.cache[k] = alloc<uint32_t>(h, N * MAX_CACHE * 3);
     }
     for (int64_t e = 0; e < n; e++) { A.seed[e] = seed; A.spawn_count[e] = 0; }
     hsim_reset(h, nullptr, MSOC_MODE_RANDOM, 0, 0, obs_out);
@@ -187,9 +185,8 @@ void hsim_get_state(HostSim *h, int64_t e, msoc_env_state *S)
     const uint32_t cnt = E.flags & FLAG_CACHE_MASK;
     S->cache_count = cnt;
     for (uint32_t j = 0; j < cnt; j++) {
-        S->cache_info[j] = A.cache_info[h->cur][(int64_t)j * A.n + e];
-        S->cache_jn[j] = A.cache_jn[h->cur][(int64_t)j * A.n + e];
-        S->cache_jt[j] = A.cache_jt[h->cur][(int64_t)j * A.n + e];
+        const uint32_t *c = A.cache[h->cur] + cache_slot(e, (int)j);
+        S->cache_info[j] = c[0]; S->cache_jn[j] = u2f(c[1]); S->cache_jt[j] = u2f(c[2]);
     }
 }
 
@@ -211,9 +208,8 @@ void hsim_set_state(HostSim *h, int64_t e, const msoc_env_state *S)
     E.flags = cnt | (((uint32_t)S->mode & 3u) << FLAG_MODE_SHIFT);
     A.spawn_count[e] = S->spawn_count; A.seed[e] = S->seed;
     for (uint32_t j = 0; j < cnt; j++) {
-        A.cache_info[h->cur][(int64_t)j * A.n + e] = S->cache_info[j];
-        A.cache_jn[h->cur][(int64_t)j * A.n + e] = S->cache_jn[j];
-        A.cache_jt[h->cur][(int64_t)j * A.n + e] = S->cache_jt[j];
+        uint32_t *c = A.cache[h->cur] + cache_slot(e, (int)j);
+        c[0] = S->cache_info[j]; c[1] = f2u(S->cache_jn[j]); c[2] = f2u(S->cache_jt[j]);
     }
     store_env(A, e, E);
 }
