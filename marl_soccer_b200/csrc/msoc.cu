@@ -539,8 +539,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     for (int i = 0; i < 5; i++) o_body[i] = take(n * sizeof(float4));
     const size_t o_ang = take(n * sizeof(float4)), o_w = take(n * sizeof(float4));
     const size_t o_bw = take(n * sizeof(float2)), o_cnt = take(n * sizeof(int4));
-    const size_t o_vb01 = take(n * sizeof(float4)), o_vb23 = take(n * sizeof(float4)), o_vb4w = take(n * sizeof(float4));
-    const size_t o_wb23 = take(n * sizeof(float2));
+    const size_t o_bias = take(n * 4 * sizeof(float4));
     const size_t o_seed = take(n * sizeof(uint64_t)), o_sc = take(n * sizeof(uint32_t));
     size_t o_cache[2];
     for (int k = 0; k < 2; k++) o_cache[k] = take(n * MAX_CACHE * 3 * sizeof(uint32_t));
@@ -562,8 +561,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     for (int i = 0; i < 5; i++) A.body[i] = (float4 *)(base + o_body[i]);
     A.ang = (float4 *)(base + o_ang); A.angvel = (float4 *)(base + o_w);
     A.ballw_ret = (float2 *)(base + o_bw); A.counters = (int4 *)(base + o_cnt);
-    A.vb01 = (float4 *)(base + o_vb01); A.vb23 = (float4 *)(base + o_vb23); A.vb4w = (float4 *)(base + o_vb4w);
-    A.wb23 = (float2 *)(base + o_wb23);
+    A.bias = (float4 *)(base + o_bias);
     A.seed = (uint64_t *)(base + o_seed); A.spawn_count = (uint32_t *)(base + o_sc);
     for (int k = 0; k < 2; k++) {
         A.cache[k] = (uint32_t *)(base + o_cache[k]);

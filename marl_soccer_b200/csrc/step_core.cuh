@@ -89,8 +89,7 @@ struct Arrays {
     float4 *angvel;    /* agent angular velocities */
     float2 *ballw_ret; /* (ball angular velocity, running episode return) */
     int4 *counters;    /* (steps, score_blue, score_red, flags) */
-    float4 *vb01, *vb23, *vb4w; /* v_bias agents 0-1, 2-3; (v_bias ball, w_bias agent 0-1) */
-    float2 *wb23;      /* w_bias agents 2-3 */
+    float4 *bias;      /* 4 per env, contiguous: v_bias agents 0-1, 2-3; (v_bias ball, w_bias agents 0-1); (w_bias agents 2-3, -, -) */
     uint64_t *seed;    /* per-env Philox key */
     uint32_t *spawn_count;
     uint32_t *cache[2]; /* arbiter cache, ping-pong between steps: entry j of env e = 3 words at cache_slot(e, j) */
@@ -230,8 +229,8 @@ MSOC_HD void load_env(const Arrays &A, int64_t e, Env &E)
     const int4 c = A.counters[e];
     E.steps = c.x; E.score_b = c.y; E.score_r = c.z; E.flags = (uint32_t)c.w;
     if (E.flags & FLAG_HAS_BIAS) {
-        const float4 b01 = A.vb01[e], b23 = A.vb23[e], b4w = A.vb4w[e];
-        const float2 w23 = A.wb23[e];
+        const float4 *bp = A.bias + 4 * e;
+        const float4 b01 = bp[0], b23 = bp[1], b4w = bp[2], w23 = bp[3];
         E.vbx[0] = b01.x; E.vby[0] = b01.y; E.vbx[1] = b01.z; E.vby[1] = b01.w;
         E.vbx[2] = b23.x; E.vby[2] = b23.y; E.vbx[3] = b23.z; E.vby[3] = b23.w;
         E.vbx[4] = b4w.x; E.vby[4] = b4w.y; E.wb[0] = b4w.z; E.wb[1] = b4w.w;
@@ -252,10 +251,11 @@ MSOC_HD void store_env(const Arrays &A, int64_t e, Env &E)
 #pragma unroll
     for (int i = 0; i < 4; i++) any_bias = any_bias || (E.wb[i] != 0.0f);
     if (any_bias) {
-        A.vb01[e] = make_float4(E.vbx[0], E.vby[0], E.vbx[1], E.vby[1]);
-        A.vb23[e] = make_float4(E.vbx[2], E.vby[2], E.vbx[3], E.vby[3]);
-        A.vb4w[e] = make_float4(E.vbx[4], E.vby[4], E.wb[0], E.wb[1]);
-        A.wb23[e] = make_float2(E.wb[2], E.wb[3]);
+        float4 *bp = A.bias + 4 * e;
+        bp[0] = make_float4(E.vbx[0], E.vby[0], E.vbx[1], E.vby[1]);
+        bp[1] = make_float4(E.vbx[2], E.vby[2], E.vbx[3], E.vby[3]);
+        bp[2] = make_float4(E.vbx[4], E.vby[4], E.wb[0], E.wb[1]);
+        bp[3] = make_float4(E.wb[2], E.wb[3], 0.0f, 0.0f);
         E.flags |= FLAG_HAS_BIAS;
     } else {
         E.flags &= ~FLAG_HAS_BIAS;
