@@ -208,7 +208,11 @@ __device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P
 enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
 
 constexpr int FAST_STRIDE = 89; /* floats of per-lane frame staging in the fast kernel (88, odd: no bank conflicts) */
-constexpr size_t FAST_SMEM_BYTES = (size_t)STEP_BLOCK * FAST_STRIDE * sizeof(float);
+#ifndef MSOC_FAST_BLOCK
+#define MSOC_FAST_BLOCK 128
+#endif
+constexpr int FAST_BLOCK = MSOC_FAST_BLOCK; /* envs (= threads) per block of the fast kernel */
+constexpr size_t FAST_SMEM_BYTES = (size_t)FAST_BLOCK * FAST_STRIDE * sizeof(float);
 #ifndef MSOC_FAST_MIN_BLOCKS
 #define MSOC_FAST_MIN_BLOCKS 4
 #endif
@@ -248,13 +252,13 @@ __device__ __forceinline__ void flush_tally(const Tally &T, double *stats, int l
     }
 }
 
-__global__ void __launch_bounds__(STEP_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fast_kernel(const __grid_constant__ StepParams P)
+__global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fast_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ float s_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
     if (blockIdx.x == 0 && tid < CTL_WORDS) P.ctl_other[tid] = 0;
-    const int64_t my_env = (int64_t)blockIdx.x * STEP_BLOCK + tid;
+    const int64_t my_env = (int64_t)blockIdx.x * FAST_BLOCK + tid;
     const bool have = my_env < P.A.n;
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
     Work W; /* never touched in contact-free mode */
@@ -292,21 +296,19 @@ __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
     const int n_light = P.ctl[CTL_LIGHT]; /* final: the fast kernel has finished */
-    const int batches = (n_light + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
+    const int batches = (n_light + 31) / 32;
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
     Work W; /* never touched in light mode */
     W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
-    __shared__ int s_batch;
 #pragma unroll 1
     while (true) {
-        /* batches are handed out dynamically: this kernel runs beside the heavy contact kernel and its blocks
-           start whenever an SM has room for them */
-        if (tid == 0) s_batch = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1);
-        __syncthreads();
-        const int b = s_batch;
-        __syncthreads();
+        /* every warp takes its own batches of 32 envs, handed out dynamically: this kernel runs beside the heavy
+           contact kernel and its blocks start whenever an SM has room for them */
+        int b = 0;
+        if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= batches) break;
-        const int idx = b * LIGHT_BLOCK + tid;
+        const int idx = b * 32 + lane;
         const bool have = idx < n_light;
         const int64_t my_env = have ? (int64_t)P.list[idx] : 0;
         bool fresh = false, ok = false;
@@ -641,8 +643,8 @@ int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, flo
     P.global_offset = h->global_offset; P.flags = flags; P.cur = h->cur;
     P.ctl = h->d_ctl + 4 * h->step_parity; P.ctl_other = h->d_ctl + 4 * (h->step_parity ^ 1); P.list = h->d_list;
     h->step_parity ^= 1;
-    const int64_t n_tiles = (h->n + STEP_BLOCK - 1) / STEP_BLOCK;
-    msoc_step_fast_kernel<<<(unsigned)n_tiles, STEP_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    const int64_t n_tiles = (h->n + FAST_BLOCK - 1) / FAST_BLOCK;
+    msoc_step_fast_kernel<<<(unsigned)n_tiles, FAST_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     /* The two contact kernels only depend on the fast kernel's list.  The heavy one (few, long, latency-bound

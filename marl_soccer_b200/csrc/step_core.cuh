@@ -961,6 +961,21 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
                       uint64_t gidx, uint32_t step_flags, Work &W, StepOut &out, int &load)
 {
     const bool FAST = MODE == MODE_FAST, LIGHT = MODE == MODE_LIGHT;
+    /* light mode: the first four cached arbiter entries (one or two sectors) are fetched right away, so that their
+       latency is covered by the prologue */
+    uint32_t pc[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) pc[k] = 0u;
+    if (LIGHT && (E.flags & FLAG_CACHE_MASK) != 0u) {
+#if defined(__CUDA_ARCH__)
+        const uint4 *q = reinterpret_cast<const uint4 *>(A.cache[cur] + cache_slot(e, 0));
+        const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
+        pc[0] = q0.x; pc[1] = q0.y; pc[2] = q0.z; pc[3] = q0.w; pc[4] = q1.x; pc[5] = q1.y; pc[6] = q1.z; pc[7] = q1.w;
+        pc[8] = q2.x; pc[9] = q2.y; pc[10] = q2.z; pc[11] = q2.w;
+#else
+        for (int k = 0; k < 12; k++) pc[k] = A.cache[cur][cache_slot(e, 0) + k];
+#endif
+    }
     /* ---- soccer_env.py:118-125: clip to [-1, 1], scale in float32 */
     float Fx[4], Fy[4], Tq[4];
     float cs[4], sn[4];
@@ -1170,15 +1185,17 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             /* cpArbiterUpdate: accumulated impulses of equal-key contacts, first-contact state */
             bool first = true;
             float jn0 = 0.0f, jt0 = 0.0f, jn1 = 0.0f, jt1 = 0.0f;
-            for (int j = 0; j < old_count; j++) {
-                const uint32_t info = oc[3 * j];
-                if ((int)(info & 63u) != l_idx) continue;
+            auto lookup = [&](uint32_t info, uint32_t wjn, uint32_t wjt) {
+                if ((int)(info & 63u) != l_idx) return;
                 if (((info >> 10) & 3u) == 0u) first = false;
                 const int key = (int)((info >> 6) & 15u);
-                const float ojn = u2f(oc[3 * j + 1]), ojt = u2f(oc[3 * j + 2]);
-                if (key == m.key[0]) { jn0 = ojn; jt0 = ojt; }
-                if (m.count > 1 && key == m.key[1]) { jn1 = ojn; jt1 = ojt; }
-            }
+                if (key == m.key[0]) { jn0 = u2f(wjn); jt0 = u2f(wjt); }
+                if (m.count > 1 && key == m.key[1]) { jn1 = u2f(wjn); jt1 = u2f(wjt); }
+            };
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < old_count) lookup(pc[3 * j], pc[3 * j + 1], pc[3 * j + 2]);
+            for (int j = 4; j < old_count; j++) lookup(oc[3 * j], oc[3 * j + 1], oc[3 * j + 2]);
             const bool two = m.count > 1;
             const float nx = m.n.x, ny = m.n.y;
             const V2 tng = vperp(m.n);
@@ -1248,15 +1265,18 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             }
         }
         /* then the untouched arbiters younger than collision_persistence (3) */
-        for (int j = 0; j < old_count; j++) {
-            const uint32_t info = oc[3 * j];
+        auto age_entry = [&](uint32_t info, uint32_t wjn, uint32_t wjt) {
             const uint32_t age = (info >> 10) & 3u;
-            if ((m.count > 0 && (int)(info & 63u) == l_idx) || age >= 2u) continue;
-            if (new_count >= MAX_CACHE) { overflow++; continue; }
+            if ((m.count > 0 && (int)(info & 63u) == l_idx) || age >= 2u) return;
+            if (new_count >= MAX_CACHE) { overflow++; return; }
             nc_[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
-            nc_[3 * new_count + 1] = oc[3 * j + 1]; nc_[3 * new_count + 2] = oc[3 * j + 2];
+            nc_[3 * new_count + 1] = wjn; nc_[3 * new_count + 2] = wjt;
             new_count++;
-        }
+        };
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < old_count) age_entry(pc[3 * j], pc[3 * j + 1], pc[3 * j + 2]);
+        for (int j = 4; j < old_count; j++) age_entry(oc[3 * j], oc[3 * j + 1], oc[3 * j + 2]);
     }
 
     if (run_contacts) {
