@@ -133,7 +133,12 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
      d_goal    (N) i8        +1 blue scored, -1 red scored, 0 none (info["goal_scored_by"])
      d_score   (N,2) i32     info["score"] of this step = (blue, red) after the goal test and before
                              any auto-reset (game/game.py:415); may be NULL
-   flags: MSOC_STEP_AUTO_RESET. */
+   flags: MSOC_STEP_AUTO_RESET.
+   Stream semantics: asynchronous; everything is ordered after the work already enqueued on `stream`, and work
+   enqueued on `stream` afterwards sees the complete step.  One step is three kernel launches (a streaming
+   contact-free kernel over all envs, then two contact kernels side by side); the handle runs one of them on an
+   internal stream that is forked from and joined back into `stream` with events, so the call is also capturable
+   in a CUDA graph. */
 int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, float *d_obs_out,
               float *d_reward, uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags,
               void *stream);
