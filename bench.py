@@ -167,6 +167,8 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs_per_gpu
