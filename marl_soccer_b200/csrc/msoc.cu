@@ -163,6 +163,25 @@ struct StepParams {
     int cur;
 };
 
+#ifdef MSOC_TIMELINE /* debug build only (tools/timeline.py): when did every batch of every step kernel run? */
+__device__ unsigned long long g_tl[1 << 18]; /* records of 4 words: kernel id, start, end (globaltimer ns), sm id */
+__device__ unsigned int g_tl_n;
+extern "C" int msoc_debug_timeline(unsigned long long *out, unsigned int *n) {
+    cudaMemcpyFromSymbol(n, g_tl_n, sizeof(unsigned int)); unsigned int z = 0; cudaMemcpyToSymbol(g_tl_n, &z, sizeof z);
+    return (int)cudaMemcpyFromSymbol(out, g_tl, sizeof g_tl);
+}
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void tl_record(int kid, unsigned long long t0) {
+    const unsigned int i = atomicAdd(&g_tl_n, 1u);
+    unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (i < (1u << 16)) { g_tl[4 * i] = (unsigned long long)kid; g_tl[4 * i + 1] = t0; g_tl[4 * i + 2] = gtime(); g_tl[4 * i + 3] = smid; }
+}
+#define MSOC_TL_BEGIN() const unsigned long long tl0 = gtime()
+#define MSOC_TL_END(kid) do { if (lane == 0) tl_record(kid, tl0); } while (0)
+#else
+#define MSOC_TL_BEGIN() do { } while (0)
+#define MSOC_TL_END(kid) do { } while (0)
+#endif
 /* Per-thread tallies for the per-rollout statistics. */
 struct Tally { int done, goals_b, goals_r, contacts, overflow, envs; float ret; };
 
@@ -258,6 +277,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
     if (blockIdx.x == 0 && tid < CTL_WORDS) P.ctl_other[tid] = 0;
+    MSOC_TL_BEGIN();
     const int64_t my_env = (int64_t)blockIdx.x * FAST_BLOCK + tid;
     const bool have = my_env < P.A.n;
     Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
@@ -279,6 +299,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     push_warp(P.ctl + CTL_LIGHT, declined && load == 0, (int)my_env, lane, [&](int i) { return P.list + i; });
     push_warp(P.ctl + CTL_HEAVY, declined && load != 0, (int)my_env, lane, [&](int i) { return P.list + (P.A.n - 1 - i); });
     flush_tally(T, P.stats, lane);
+    if ((blockIdx.x & 15) == 0 && warp == 0) MSOC_TL_END(0);
 }
 
 /* Light envs (exactly one agent x wall candidate pair, ~82 % of the contact envs): thread t of a batch steps
@@ -311,6 +332,7 @@ __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light
         const int idx = b * 32 + lane;
         const bool have = idx < n_light;
         const int64_t my_env = have ? (int64_t)P.list[idx] : 0;
+        MSOC_TL_BEGIN();
         bool fresh = false, ok = false;
         int load = 0;
         {
@@ -324,6 +346,7 @@ __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light
         if (mask) write_obs_tile<FAST_STRIDE>(reinterpret_cast<const float2 *>(P.obs_in), reinterpret_cast<float2 *>(P.obs_out), s_warp,
                                               mask, fmask, my_env, lane);
         __syncwarp(); /* the staging area is rewritten by the next batch */
+        MSOC_TL_END(1);
     }
     flush_tally(T, P.stats, lane);
 }
@@ -374,6 +397,7 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         const bool have = idx < n_heavy;
         int64_t my_env = 0;
         if (have) my_env = (int64_t)P.list[P.A.n - 1 - idx];
+        MSOC_TL_BEGIN();
         bool fresh = false, ok = false;
         int load = 0;
         if (lane == 0) *W.pool_count = 0; /* the warp's contact pool is empty */
@@ -389,6 +413,7 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         __syncwarp();
         if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
         __syncwarp();
+        MSOC_TL_END(2);
     }
     flush_tally(T, P.stats, lane);
 }

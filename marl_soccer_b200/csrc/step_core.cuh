@@ -51,6 +51,9 @@ constexpr float TWO_PI_LO = -1.74845553e-7f;      /* 2 pi - TWO_PI_HI */
 constexpr float SLOP = 0.1f;                      /* cpSpace collisionSlop */
 constexpr float BIAS_COEF_OVER_DT = 0.1f * 60.0f; /* (1 - collisionBias^dt) / dt, collisionBias = 0.9^60 */
 constexpr int SOLVER_ITERS = 10;                  /* cpSpace iterations default */
+/* squared centre distances beyond which two agents / the ball and an agent cannot touch (circumscribed circles + 0.01 px) */
+constexpr float AA_REACH2 = (float)((2.0 * 15.0 * 1.4142135623730951 + 0.01) * (2.0 * 15.0 * 1.4142135623730951 + 0.01));
+constexpr float BA_REACH2 = (float)((15.0 * 1.4142135623730951 + 10.0 + 0.01) * (15.0 * 1.4142135623730951 + 10.0 + 0.01));
 
 constexpr int N_AGENTS = 4, BALL = 4, STATIC_BODY = 5;
 constexpr int FRAME = 22, OBS = 66;
@@ -1038,7 +1041,10 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #pragma unroll
             for (int j = i + 1; j < 4; j++) {
                 const float rr = R[i] + R[j];
-                if (fabsf(E.px[i] - E.px[j]) <= rr && fabsf(E.py[i] - E.py[j]) <= rr) m_aa |= 1u << p;
+                const float dx = E.px[i] - E.px[j], dy = E.py[i] - E.py[j];
+                /* bounding boxes overlap AND the circumscribed circles (radius 15 sqrt 2) do: both are necessary for
+                   the boxes to touch; the second test spares the general path most near misses */
+                if (fabsf(dx) <= rr && fabsf(dy) <= rr && dx * dx + dy * dy <= AA_REACH2) m_aa |= 1u << p;
                 p++;
             }
         }
@@ -1046,7 +1052,8 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const float rr = R[i] + BALL_R;
-        if (fabsf(E.px[i] - E.px[4]) <= rr && fabsf(E.py[i] - E.py[4]) <= rr) m_ba |= 1u << i;
+        const float dx = E.px[i] - E.px[4], dy = E.py[i] - E.py[4];
+        if (fabsf(dx) <= rr && fabsf(dy) <= rr && dx * dx + dy * dy <= BA_REACH2) m_ba |= 1u << i;
     }
     {
         const float x = E.px[4], y = E.py[4], r = BALL_R;
