@@ -406,10 +406,11 @@ MSOC_HD void make_box(float cs, float sn, V2 off, Box &b)
 }
 
 /* Closest features of two convex polygons (a segment is a 2-gon): the (n, d) Chipmunk's GJK
-   (separated) / EPA (overlapping) converge to.  nA[k] / nB[k] are unit outward normals of the edge
+   (separated) / EPA (overlapping) converge to -- exact whenever d <= reach; for shapes further apart than `reach`
+   only a lower bound d > reach is returned.  nA[k] / nB[k] are unit outward normals of the edge
    k -> k+1, il2 = 1/|edge|^2 (all edges of one shape have the same length here). */
 template <int NA, int NB>
-MSOC_HD void closest_convex(const V2 *A, const V2 *nA, float il2A, const V2 *B, const V2 *nB, float il2B, V2 &n_out, float &d_out)
+MSOC_HD void closest_convex(const V2 *A, const V2 *nA, float il2A, const V2 *B, const V2 *nB, float il2B, float reach, V2 &n_out, float &d_out)
 {
     float best = -INFINITY; V2 bn = mk(0.0f, 0.0f);
 #pragma unroll
@@ -427,6 +428,9 @@ MSOC_HD void closest_convex(const V2 *A, const V2 *nA, float il2A, const V2 *B, 
         if (s > best) { best = s; bn = vneg(nB[k]); }
     }
     if (best <= 0.0f) { n_out = bn; d_out = best; return; }
+    /* separated along a face normal by more than the caller cares about: the distance is at least that (the caller
+       only asks "closer than reach?"), so the closest-feature search below is not needed */
+    if (best > reach) { n_out = bn; d_out = best; return; }
     float bd2 = INFINITY; V2 bdel = bn;
 #pragma unroll
     for (int k = 0; k < NA; k++) {
@@ -551,7 +555,7 @@ MSOC_HD void collide_segment_box(const Seg &g, V2 c, float cs, float sn, Manifol
         if (s1 > s0) { n = vneg(g.n); d = s1; } else { n = g.n; d = s0; }
     } else {
         const V2 bn[4] = {box.nrm[1], box.nrm[2], box.nrm[3], box.nrm[0]};
-        closest_convex<2, 4>(sv, sn2, g.il2, box.v, bn, 1.0f / 900.0f, n, d);
+        closest_convex<2, 4>(sv, sn2, g.il2, box.v, bn, 1.0f / 900.0f, g.r + 1e-3f, n, d);
     }
     m.count = 0;
     if (d - g.r <= 0.0f) {
@@ -569,7 +573,7 @@ MSOC_HD void collide_box_box(float csa, float sna, float csb, float snb, V2 off,
     const V2 an[4] = {A.nrm[1], A.nrm[2], A.nrm[3], A.nrm[0]};
     const V2 bn[4] = {B.nrm[1], B.nrm[2], B.nrm[3], B.nrm[0]};
     V2 n; float d;
-    closest_convex<4, 4>(A.v, an, 1.0f / 900.0f, B.v, bn, 1.0f / 900.0f, n, d);
+    closest_convex<4, 4>(A.v, an, 1.0f / 900.0f, B.v, bn, 1.0f / 900.0f, 1e-3f, n, d);
     m.count = 0;
     if (d <= 0.0f) contact_points(support_edge_poly(A, n), support_edge_poly(B, vneg(n)), n, d, m);
 }
