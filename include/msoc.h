@@ -137,8 +137,9 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
    Stream semantics: asynchronous; everything is ordered after the work already enqueued on `stream`, and work
    enqueued on `stream` afterwards sees the complete step.  One step is three kernel launches (a streaming
    contact-free kernel over all envs, then two contact kernels side by side); the handle runs one of them on an
-   internal stream that is forked from and joined back into `stream` with events, so the call is also capturable
-   in a CUDA graph. */
+   internal stream that is forked from and joined back into `stream` with events.  The handle alternates between two
+   halves of its arbiter cache and of its scheduling counters from one call to the next (host-side state), so a CUDA
+   graph must capture an EVEN number of consecutive steps to be replayable. */
 int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, float *d_obs_out,
               float *d_reward, uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags,
               void *stream);

@@ -362,7 +362,10 @@ static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch
                                memory are handed to the light kernel warp by warp as the heavy batches finish */
 #endif
 constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
-constexpr int HEAVY_MIN_BLOCKS = STEP_MIN_BLOCKS * STEP_BLOCK / HEAVY_BLOCK; /* the same number of resident warps */
+#ifndef MSOC_HEAVY_MIN_BLOCKS
+#define MSOC_HEAVY_MIN_BLOCKS 5 /* register cap 204: ptxas settles on 168 without spills (with 6 it spills 48 B); 6 blocks are resident all the same */
+#endif
+constexpr int HEAVY_MIN_BLOCKS = MSOC_HEAVY_MIN_BLOCKS;
 constexpr size_t STEP_SMEM_BYTES = (size_t)HEAVY_BLOCK * ENV_STRIDE * sizeof(float);
 
 __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
