@@ -565,10 +565,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     const size_t n = (size_t)n_envs;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-    size_t o_body[5];
-    for (int i = 0; i < 5; i++) o_body[i] = take(n * sizeof(float4));
-    const size_t o_ang = take(n * sizeof(float4)), o_w = take(n * sizeof(float4));
-    const size_t o_bw = take(n * sizeof(float2)), o_cnt = take(n * sizeof(int4));
+    const size_t o_bodies = take(n * 5 * sizeof(float4)), o_misc = take(n * 4 * sizeof(float4));
     const size_t o_bias = take(n * 4 * sizeof(float4));
     const size_t o_seed = take(n * sizeof(uint64_t)), o_sc = take(n * sizeof(uint32_t));
     size_t o_cache[2];
@@ -588,9 +585,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     char *base = (char *)h->slab;
     Arrays &A = h->A;
     A.n = n_envs;
-    for (int i = 0; i < 5; i++) A.body[i] = (float4 *)(base + o_body[i]);
-    A.ang = (float4 *)(base + o_ang); A.angvel = (float4 *)(base + o_w);
-    A.ballw_ret = (float2 *)(base + o_bw); A.counters = (int4 *)(base + o_cnt);
+    A.bodies = (float4 *)(base + o_bodies); A.misc = (float4 *)(base + o_misc);
     A.bias = (float4 *)(base + o_bias);
     A.seed = (uint64_t *)(base + o_seed); A.spawn_count = (uint32_t *)(base + o_sc);
     for (int k = 0; k < 2; k++) {
@@ -738,7 +733,7 @@ int msoc_read_counters(msoc_handle *h, int32_t *h_score, int32_t *h_steps, void 
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<int4> tmp((size_t)h->n);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->A.counters, (size_t)h->n * sizeof(int4), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpy2DAsync(tmp.data(), sizeof(int4), h->A.misc + 2, 4 * sizeof(float4), sizeof(int4), (size_t)h->n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < h->n; i++) {
         if (h_steps) h_steps[i] = tmp[(size_t)i].x;

@@ -87,11 +87,12 @@ struct SimCfg {
 /* struct-of-arrays state of N envs (device memory in the product, host memory in tests/hostsim) */
 struct Arrays {
     int64_t n;
-    float4 *body[5];   /* (px, py, vx, vy) of agent_0..3, ball */
-    float4 *ang;       /* agent angles, wrapped */
-    float4 *angvel;    /* agent angular velocities */
-    float2 *ballw_ret; /* (ball angular velocity, running episode return) */
-    int4 *counters;    /* (steps, score_blue, score_red, flags) */
+    /* Records of an env are contiguous: the contact kernels touch scattered envs, and a record that fills whole 32-byte
+       sectors costs them half the DRAM traffic of one 16-byte field per array (the fast kernel, which walks consecutive
+       envs, reads the same bytes either way). */
+    float4 *bodies;    /* 5 per env: (px, py, vx, vy) of agent_0..3, ball */
+    float4 *misc;      /* 4 per env: agent angles (wrapped); agent angular velocities; (steps, score_blue, score_red, flags)
+                          as bits; (ball angular velocity, running episode return, -, -) */
     float4 *bias;      /* 4 per env, contiguous: v_bias agents 0-1, 2-3; (v_bias ball, w_bias agents 0-1); (w_bias agents 2-3, -, -) */
     uint64_t *seed;    /* per-env Philox key */
     uint32_t *spawn_count;
@@ -216,20 +217,37 @@ MSOC_HD_NOINLINE uint32_t spawn_positions(int mode, uint64_t seed, uint64_t gidx
     return spawn_count + 1;
 }
 
+MSOC_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+MSOC_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
 /* -------------------------------------------------------------------------------- state load/store */
 MSOC_HD void load_env(const Arrays &A, int64_t e, Env &E)
 {
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        const float4 b = A.body[i][e];
+        const float4 b = A.bodies[e * 5 + i];
         E.px[i] = b.x; E.py[i] = b.y; E.vx[i] = b.z; E.vy[i] = b.w;
     }
-    const float4 a = A.ang[e], w = A.angvel[e];
+    const float4 a = A.misc[e * 4], w = A.misc[e * 4 + 1], cbits = A.misc[e * 4 + 2], brw = A.misc[e * 4 + 3];
+    const float2 br = make_float2(brw.x, brw.y);
+    const int4 c = make_int4((int)f2u(cbits.x), (int)f2u(cbits.y), (int)f2u(cbits.z), (int)f2u(cbits.w));
     E.ang[0] = a.x; E.ang[1] = a.y; E.ang[2] = a.z; E.ang[3] = a.w;
     E.w[0] = w.x; E.w[1] = w.y; E.w[2] = w.z; E.w[3] = w.w;
-    const float2 br = A.ballw_ret[e];
     E.w[4] = br.x; E.ep_return = br.y;
-    const int4 c = A.counters[e];
     E.steps = c.x; E.score_b = c.y; E.score_r = c.z; E.flags = (uint32_t)c.w;
     if (E.flags & FLAG_HAS_BIAS) {
         const float4 *bp = A.bias + 4 * e;
@@ -264,11 +282,11 @@ MSOC_HD void store_env(const Arrays &A, int64_t e, Env &E)
         E.flags &= ~FLAG_HAS_BIAS;
     }
 #pragma unroll
-    for (int i = 0; i < 5; i++) A.body[i][e] = make_float4(E.px[i], E.py[i], E.vx[i], E.vy[i]);
-    A.ang[e] = make_float4(E.ang[0], E.ang[1], E.ang[2], E.ang[3]);
-    A.angvel[e] = make_float4(E.w[0], E.w[1], E.w[2], E.w[3]);
-    A.ballw_ret[e] = make_float2(E.w[4], E.ep_return);
-    A.counters[e] = make_int4(E.steps, E.score_b, E.score_r, (int)E.flags);
+    for (int i = 0; i < 5; i++) A.bodies[e * 5 + i] = make_float4(E.px[i], E.py[i], E.vx[i], E.vy[i]);
+    A.misc[e * 4] = make_float4(E.ang[0], E.ang[1], E.ang[2], E.ang[3]);
+    A.misc[e * 4 + 1] = make_float4(E.w[0], E.w[1], E.w[2], E.w[3]);
+    A.misc[e * 4 + 2] = make_float4(u2f((uint32_t)E.steps), u2f((uint32_t)E.score_b), u2f((uint32_t)E.score_r), u2f(E.flags));
+    A.misc[e * 4 + 3] = make_float4(E.w[4], E.ep_return, 0.0f, 0.0f);
 }
 
 /* ----------------------------------------------------------------------------- observation frame */
@@ -652,22 +670,6 @@ constexpr int SCR = 1;
 constexpr int CON_FS = CON_FAST * SCR; /* distance between two fields of a shared-memory contact */
 constexpr int BODY_FS = 5 * SCR;       /* distance between two fields of a body */
 
-MSOC_HD uint32_t f2u(float f)
-{
-#if defined(__CUDA_ARCH__)
-    return __float_as_uint(f);
-#else
-    uint32_t u; memcpy(&u, &f, 4); return u;
-#endif
-}
-MSOC_HD float u2f(uint32_t u)
-{
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(u);
-#else
-    float f; memcpy(&f, &u, 4); return f;
-#endif
-}
 
 constexpr int GEOM_WORDS = 22; /* px[5] py[5] cos[4] sin[4] angle[4]: parked while the contact path runs */
 enum { GF_PX = 0, GF_PY = 5, GF_CS = 10, GF_SN = 14, GF_ANG = 18 };

@@ -63,9 +63,7 @@ HostSim *hsim_create(const msoc_config *cfg, int64_t n, uint64_t seed, uint64_t 
     Arrays &A = h->A;
     A.n = n;
     const size_t N = (size_t)n;
-    for (int i = 0; i < 5; i++) A.body[i] = alloc<float4>(h, N);
-    A.ang = alloc<float4>(h, N); A.angvel = alloc<float4>(h, N);
-    A.ballw_ret = alloc<float2>(h, N); A.counters = alloc<int4>(h, N);
+    A.bodies = alloc<float4>(h, N * 5); A.misc = alloc<float4>(h, N * 4);
     A.bias = alloc<float4>(h, N * 4);
     A.seed = alloc<uint64_t>(h, N); A.spawn_count = alloc<uint32_t>(h, N);
     for (int k = 0; k < 2; k++) {
