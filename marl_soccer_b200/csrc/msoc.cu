@@ -2,13 +2,13 @@
  * msoc.cu -- B200 (sm_100a) kernels and the C-ABI (include/msoc.h) of the batched 2v2 soccer
  * simulator.  Replaces the reference's per-env Python/pymunk update loop
  * (soccer_simulation/marl_vecenv.py:30-68 -> soccer_env.py:100-154 -> game/game.py:378-437 ->
- * pymunk Space.step) with ONE fused kernel per vectorised step.
+ * pymunk Space.step) with one fused device step per vectorised step: three launches, see "The fused step".
  *
- * Data layout: struct-of-arrays over N envs, float4-packed (msoc::Arrays in step_core.cuh); one
- * thread owns one env, one warp owns a tile of 32 consecutive envs.  State loads/stores are
- * 16 B per lane, fully coalesced.  Observations (N,4,66) are written per warp tile: the new 22-float
- * frames are staged through shared memory and the 3-frame stack is shifted with coalesced 8-byte
- * accesses (rows of 264 B are 8-byte aligned), so every DRAM sector is fully used.
+ * Data layout: per-env records of float4s over N envs (msoc::Arrays in step_core.cuh); one thread owns
+ * one env, one warp a batch of 32 envs (consecutive in the streaming kernel, listed in the contact
+ * kernels).  Observations (N,4,66) are written per warp: the new 22-float frames are staged through
+ * shared memory and the 3-frame stack is shifted with coalesced 8-byte accesses (rows of 264 B are
+ * 8-byte aligned), so every DRAM sector of an env's 1 056-byte block is written once.
  *
  * There is no CPU fallback in this library: every entry point needs a CUDA device.
  */

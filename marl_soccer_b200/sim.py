@@ -1,6 +1,6 @@
 """BatchedSoccerSim -- the device-resident form of the reference's env stack.
 
-N independent 2v2 soccer envs live in struct-of-arrays HBM buffers owned by one C-ABI handle
+N independent 2v2 soccer envs live in HBM buffers (contiguous per-env records) owned by one C-ABI handle
 (include/msoc.h); one fused CUDA kernel per `step` replaces
 SyncMultiAgentVecEnv.step -> SoccerEnv.step -> Game.step -> pymunk Space.step
 (soccer_simulation/marl_vecenv.py:30-68, soccer_env.py:100-154, game/game.py:378-437).
