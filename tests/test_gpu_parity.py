@@ -141,3 +141,43 @@ def test_full_size_invariants_65536():
     assert total_done == n
     stats = sim.stats()
     assert stats["episodes"] == n and stats["env_steps"] == 8 * n and stats["contact_overflow"] == 0
+
+
+def test_free_running_episode_statistics_match_the_oracle():
+    """Free-running rollouts through contacts diverge chaotically between fp32 and fp64 (a contact one step earlier or
+    later), so whole episodes are compared as populations: 4 096 envs x 1 000 steps (one full episode incl. the corner
+    spawns, truncation and auto-reset) with the same i.i.d. actions on both sides; contacts per env-step, goals, episode
+    returns and the distribution of the final observations must agree within sampling error."""
+    n, steps = 4096, 1001
+    sim = Dev(n, P.CONFIG, seed=21)
+    ora = O.OracleVec(n, P.CONFIG, seed=21)
+    sim.reset(O.MODE_FULL_RANDOM, seed=4)
+    ora.reset(O.MODE_FULL_RANDOM, seed=4)
+    sim.stats(reset=True)
+    rng = np.random.default_rng(8)
+    ret_d, ret_o = np.zeros(n), np.zeros(n)
+    goals_d = goals_o = 0
+    done_d = done_o = 0
+    contacts_o = 0
+    for t in range(steps):
+        act = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)
+        o_d, r_d, d_d, g_d = sim.step(act)
+        o_o, r_o, d_o, g_o = ora.step(act, nthreads=8)
+        assert np.array_equal(d_d, d_o), "truncation is a pure step count: it must agree exactly"
+        ret_d += r_d[:, 0]; ret_o += r_o[:, 0]
+        goals_d += int(np.abs(g_d).sum()); goals_o += int(np.abs(g_o).sum())
+        done_d += int(d_d.sum()); done_o += int(d_o.sum())
+    st = sim.stats()
+    assert done_d == done_o == n and st["episodes"] == n and st["contact_overflow"] == 0
+    # goals: Poisson counts of a few dozen
+    assert abs(goals_d - goals_o) <= 4 * np.sqrt(max(goals_o, 1)) + 4, (goals_d, goals_o)
+    # episode returns: same mean within 4 standard errors, same spread within 10 %
+    se = np.sqrt(ret_o.var() / n + ret_d.var() / n)
+    assert abs(ret_d.mean() - ret_o.mean()) <= 4 * se + 1e-3, (ret_d.mean(), ret_o.mean(), se)
+    assert abs(ret_d.std() / ret_o.std() - 1) < 0.1, (ret_d.std(), ret_o.std())
+    # where the agents and the ball end up: mean of every observation feature of the last step
+    diff = np.abs(o_d.reshape(n, -1).mean(0) - o_o.reshape(n, -1).mean(0))
+    spread = o_o.reshape(n, -1).std(0) / np.sqrt(n)
+    assert np.all(diff <= 6 * spread + 2e-3), float((diff / (6 * spread + 2e-3)).max())
+    print("episode statistics: goals", goals_d, goals_o, "mean return", ret_d.mean(), ret_o.mean(),
+          "contacts/env-step (device)", st["contacts"] / st["env_steps"])
