@@ -213,17 +213,19 @@ __device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P
                              mode and its warp writes the observation rows.  No contact code is compiled into
                              it: few registers, small shared memory, small instruction footprint -> many
                              resident warps to hide the HBM latency.  Envs whose broad phase finds a candidate
-                             pair (~28 % in the benchmark mix) write nothing and are appended, one atomic per
+                             pair (~27 % in the benchmark mix) write nothing and are appended, one atomic per
                              warp and class, to the step's contact list: light (exactly one agent x wall pair,
                              the bulk) from the front, heavy (anything else) from the back.
-   msoc_step_light_kernel    batches of 128 light envs, thread per env: one narrow-phase call and a register-only
-                             single-body impulse solver (at most two contacts); again no solver scratch.
-   msoc_step_contact_kernel  a persistent grid takes batches of 128 heavy envs and every thread steps one of
-                             them in full mode: narrow phase over all candidate pairs, arbiter cache,
+   msoc_step_light_kernel    every warp of a persistent grid takes batches of 32 light envs, thread per env: one
+                             narrow-phase call and a register-only single-body impulse solver (at most two
+                             contacts); again no solver scratch.
+   msoc_step_contact_kernel  every warp of a persistent grid takes batches of 32 heavy envs and every thread steps
+                             one of them in full mode: narrow phase over all candidate pairs, arbiter cache,
                              10-iteration impulse solver with bodies and contacts in shared memory; its warp
                              writes the rows.
    The divergent, latency-bound contact work therefore always runs on full warps of similar work, and each
-   kind of work gets the register / shared-memory budget (hence the occupancy) that suits it. */
+   kind of work gets the register / shared-memory budget (hence the occupancy) that suits it.  The two contact
+   kernels only depend on the fast kernel's lists and are launched on two streams (msoc_step). */
 enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
 
 constexpr int FAST_STRIDE = 89; /* floats of per-lane frame staging in the fast kernel (88, odd: no bank conflicts) */
