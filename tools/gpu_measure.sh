@@ -11,10 +11,11 @@ SMI=$!
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench.json
 kill $SMI
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_reference.json
-SHORT="python bench.py --steps 40 --warmup 5 --preroll 60 --e2e-steps 2 --no-cpu-baseline"
+# the bench workload itself (same 1000-step pre-roll, so the same steady-state env mix), fewer timed steps
+SHORT="python bench.py --steps 40 --warmup 5 --e2e-steps 2 --no-cpu-baseline"
 $SHORT > gpurun_out/${TAG}_short_plain.json 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 250 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:msoc_step -s 3030 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $SHORT > gpurun_out/${TAG}_short_plain2.json 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:msoc_step -s 300 -c 3 -o gpurun_out/${TAG}_step_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:msoc_step -s 3030 -c 3 -o gpurun_out/${TAG}_step_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log
 ls -la gpurun_out | tail -15
