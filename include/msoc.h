@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MSOC_VERSION 1
+#define MSOC_VERSION 2
 #define MSOC_N_AGENTS 4
 #define MSOC_ACT_DIM 3
 #define MSOC_FRAME 22   /* soccer_env.py:39 _frame_size */
@@ -85,6 +85,19 @@ typedef struct msoc_env_state {
     uint32_t cache_info[MSOC_MAX_CACHE];
     float cache_jn[MSOC_MAX_CACHE];
     float cache_jt[MSOC_MAX_CACHE];
+    /* Observation history (the 3-frame deques of soccer_env.py:69,92-96,134-137).  The simulator does not keep
+       emitted frames; it keeps the POSES they were made from and rebuilds the stack every step (bit-identical:
+       same arithmetic, same fp32 inputs).  hist_*[0] is the pose behind frame t-2, hist_*[1] behind frame t-1
+       (the newest emitted frame; normally the state itself).  msoc_get_state always fills them (hist_valid = 1).
+       msoc_set_state with hist_valid = 0 leaves the emitted history alone, like poking the bodies of the
+       reference's Game (the next observation still shows the frames emitted before the poke); with
+       hist_valid = 1 it installs both poses (checkpoint restore, parity injection). */
+    uint32_t hist_valid;
+    uint32_t reserved0;
+    float hist_pos[2][5][2];
+    float hist_vel[2][4][2];
+    float hist_ang[2][4];
+    float hist_angvel[2][4];
 } msoc_env_state;
 
 /* Per-rollout statistics accumulated on the device since the last msoc_stats_read(.., reset=1)
@@ -96,7 +109,8 @@ typedef struct msoc_stats {
     double env_steps;
     double contacts;          /* contacts solved */
     double contact_overflow;  /* contacts dropped because an env exceeded MSOC_MAX_CONTACTS */
-    double reserved;
+    double nonfinite_actions; /* env-steps whose action block held a NaN/Inf (soccer_env.py:116-117 raises; the
+                                 device path clips -- NaN acts as -1 -- and counts) */
 } msoc_stats;
 
 typedef struct msoc_handle msoc_handle;
@@ -126,8 +140,8 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
 /* Replaces: SyncMultiAgentVecEnv.step -> SoccerEnv.step -> Game.step -> Space.step(1/60)
    (marl_vecenv.py:30-68, soccer_env.py:100-154, game/game.py:378-437).
      d_actions (N,4,3) f32 in [-1,1] (clipped, soccer_env.py:119)
-     d_obs_in  (N,4,66) f32  previous stacked observation (frames t-2,t-1 are read from it)
-     d_obs_out (N,4,66) f32  new stacked observation; may alias d_obs_in
+     d_obs_out (N,4,66) f32  new stacked observation [frame t-2 | frame t-1 | frame t] per agent; write-only: the
+                             history lives in the handle as poses (see msoc_env_state), not in this buffer
      d_reward  (N,2) f32     blue agents' reward (red is always 0.0, soccer_env.py:141-146)
      d_done    (N) u8        truncation flag (soccer_env.py:148)
      d_goal    (N) i8        +1 blue scored, -1 red scored, 0 none (info["goal_scored_by"])
@@ -137,18 +151,24 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
    Stream semantics: asynchronous; everything is ordered after the work already enqueued on `stream`, and work
    enqueued on `stream` afterwards sees the complete step.  One step is three kernel launches (a streaming
    contact-free kernel over all envs, then two contact kernels side by side); the handle runs one of them on an
-   internal stream that is forked from and joined back into `stream` with events.  The handle alternates between two
-   halves of its arbiter cache and of its scheduling counters from one call to the next (host-side state), so a CUDA
-   graph must capture an EVEN number of consecutive steps to be replayable. */
-int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, float *d_obs_out,
+   internal stream that is forked from and joined back into `stream` with events.  Which half of the ping-pong state
+   is current is a counter in device memory that the kernels advance themselves, so a CUDA graph may capture any
+   number of consecutive steps and be replayed any number of times. */
+int msoc_step(msoc_handle *h, const float *d_actions, float *d_obs_out,
               float *d_reward, uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags,
               void *stream);
 
 /* Same call with HOST buffers (the NumPy drop-in path, marl_vecenv.py:62-68): copies actions
-   H2D, steps, copies obs/reward/done/goal D2H and synchronises.  The observation history
-   lives in an internal device buffer.  Pinned host memory is used as given. */
+   H2D, steps, copies obs/reward/done/goal D2H and synchronises; NULL output pointers are skipped.  Large batches are
+   cut into up to 8 chunks on two internal streams so that the H2D copy and the kernels of one chunk overlap the D2H
+   copies of the previous one.  Pinned host memory is used as given. */
 int msoc_step_host(msoc_handle *h, const float *h_actions, float *h_obs, float *h_reward,
                    uint8_t *h_done, int8_t *h_goal, int32_t *h_score, uint32_t flags, void *stream);
+/* The same step, but only the NEWEST frame comes back: h_frames (N,4,22) f32 = 352 B per env instead of 1 056.  The
+   caller owns the 3-frame stack exactly as soccer_env.py:130-140 does (append the new frame; after a truncation with
+   MSOC_STEP_AUTO_RESET the new frame is frame 0 of the next episode and fills all three slots, soccer_env.py:92-96). */
+int msoc_step_host_frames(msoc_handle *h, const float *h_actions, float *h_frames, float *h_reward,
+                          uint8_t *h_done, int8_t *h_goal, int32_t *h_score, uint32_t flags, void *stream);
 int msoc_reset_host(msoc_handle *h, const uint8_t *h_mask, int mode, int has_seed, uint64_t seed,
                     float *h_obs, void *stream);
 
@@ -175,11 +195,9 @@ typedef struct msoc_buffers {
 } msoc_buffers;
 int msoc_device_buffers(msoc_handle *h, msoc_buffers *out);
 
-/* Rows of the INTERNAL observation history used by the *_host entry points (the 3-frame buffers
-   of soccer_env.py:69, per env 4 x 66 floats); synchronous.  Lets a caller checkpoint / inject the
-   history together with msoc_get_state / msoc_set_state. */
+/* Rows of the handle's INTERNAL observation buffer (the last stacked observation the *_host entry points produced,
+   per env 4 x 66 floats) for a list of envs; synchronous. */
 int msoc_get_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, float *h_obs);
-int msoc_set_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, const float *h_obs);
 
 /* Statistics: d_out receives 8 doubles (msoc_stats layout) on the device, stream-ordered, ready to
    be all-reduced with NCCL; reset != 0 zeroes the accumulators afterwards. */

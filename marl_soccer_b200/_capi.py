@@ -20,7 +20,7 @@ STEP_AUTO_RESET = 1
 EXPORTS = (
     "msoc_last_error", "msoc_version", "msoc_create", "msoc_destroy", "msoc_num_envs", "msoc_reset",
     "msoc_step", "msoc_step_host", "msoc_reset_host", "msoc_read_counters", "msoc_get_state",
-    "msoc_set_state", "msoc_get_obs_host", "msoc_set_obs_host", "msoc_stats_device", "msoc_stats_read",
+    "msoc_set_state", "msoc_get_obs_host", "msoc_step_host_frames", "msoc_stats_device", "msoc_stats_read",
     "msoc_launch_count", "msoc_device_buffers",
 )
 
@@ -42,13 +42,17 @@ class MsocEnvState(C.Structure):
         ("spawn_count", C.c_uint32), ("cache_count", C.c_uint32), ("seed", C.c_uint64),
         ("cache_info", C.c_uint32 * MAX_CACHE), ("cache_jn", C.c_float * MAX_CACHE),
         ("cache_jt", C.c_float * MAX_CACHE),
+        # observation history as poses (include/msoc.h): [0] behind frame t-2, [1] behind frame t-1
+        ("hist_valid", C.c_uint32), ("reserved0", C.c_uint32),
+        ("hist_pos", C.c_float * 2 * 5 * 2), ("hist_vel", C.c_float * 2 * 4 * 2),
+        ("hist_ang", C.c_float * 4 * 2), ("hist_angvel", C.c_float * 4 * 2),
     ]
 
 
 class MsocStats(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "episodes", "episode_return_sum", "goals_blue", "goals_red", "env_steps", "contacts",
-        "contact_overflow", "reserved")]
+        "contact_overflow", "nonfinite_actions")]
 
 
 def make_config(config: dict) -> MsocConfig:
@@ -97,14 +101,14 @@ def declare(L) -> None:
     L.msoc_num_envs.argtypes = [vp]
     L.msoc_num_envs.restype = i64
     L.msoc_reset.argtypes = [vp, vp, C.c_int, C.c_int, u64, vp, vp]
-    L.msoc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.msoc_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp]
     L.msoc_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.msoc_step_host_frames.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, vp]
     L.msoc_reset_host.argtypes = [vp, vp, C.c_int, C.c_int, u64, vp, vp]
     L.msoc_read_counters.argtypes = [vp, vp, vp, vp]
     L.msoc_get_state.argtypes = [vp, vp, i64, vp]
     L.msoc_set_state.argtypes = [vp, vp, i64, vp]
     L.msoc_get_obs_host.argtypes = [vp, vp, i64, vp]
-    L.msoc_set_obs_host.argtypes = [vp, vp, i64, vp]
     L.msoc_device_buffers.argtypes = [vp, C.POINTER(MsocBuffers)]
     L.msoc_stats_device.argtypes = [vp, vp, C.c_int, vp]
     L.msoc_stats_read.argtypes = [vp, C.POINTER(MsocStats), C.c_int, vp]

@@ -4,11 +4,13 @@
  * (soccer_simulation/marl_vecenv.py:30-68 -> soccer_env.py:100-154 -> game/game.py:378-437 ->
  * pymunk Space.step) with one fused device step per vectorised step: three launches, see "The fused step".
  *
- * Data layout: per-env records of float4s over N envs (msoc::Arrays in step_core.cuh); one thread owns
- * one env, one warp a batch of 32 envs (consecutive in the streaming kernel, listed in the contact
- * kernels).  Observations (N,4,66) are written per warp: the new 22-float frames are staged through
- * shared memory and the 3-frame stack is shifted with coalesced 8-byte accesses (rows of 264 B are
- * 8-byte aligned), so every DRAM sector of an env's 1 056-byte block is written once.
+ * Data layout: one 128-byte record per env in each of three rotating buffers (msoc::Arrays in step_core.cuh);
+ * one thread owns one env while it is stepped, one warp a batch of 32 envs (consecutive in the streaming kernel,
+ * listed in the contact kernels).  The stacked observations (N,4,66) are never read back: once a warp has stored
+ * the new states, the three buffers hold the poses behind the three frames of the stack, and the warp rebuilds
+ * the observations of its envs from them -- four lanes per env (one per agent), eight envs at a time, staged in
+ * shared memory in the layout of the output and written as whole 1 056-byte blocks with 16-byte stores, so that
+ * every DRAM sector is written exactly once and in full.
  *
  * There is no CPU fallback in this library: every entry point needs a CUDA device.
  */
@@ -51,13 +53,18 @@ struct DeviceGuard {
 };
 
 /* ------------------------------------------------------------------------------------ handle */
+constexpr int MAX_CHUNKS = 8; /* pipeline stages of the host-buffer step */
+/* control block in device memory (ints): two sets of list counters that alternate between steps, the step counters
+   that select the ping-pong halves, one set of list counters per pipeline chunk of the host-buffer step */
+enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
+enum { CTL_STEP_FAST = 8, CTL_STEP_CONTACT = 9, CTL_CHUNK0 = 16, CTL_TOTAL = CTL_CHUNK0 + CTL_WORDS * MAX_CHUNKS };
+
 struct msoc_handle {
     int device;
     int64_t n;
     uint64_t global_offset;
     SimCfg cfg;
     Arrays A;
-    int cur; /* which half of the ping-pong arbiter cache is current */
     int sm_count, blocks_per_sm, light_blocks_per_sm; /* persistent grids of the contact and light kernels */
     void *slab;
     /* internal I/O buffers of the host-buffer API */
@@ -66,101 +73,47 @@ struct msoc_handle {
     int8_t *d_goal;
     int32_t *d_score;
     double *d_stats; /* 8 doubles, msoc_stats layout */
-    int *d_ctl;  /* 2 x CTL_WORDS counters of the step kernels, alternating between steps */
-    int *d_list; /* n ints: contact list of the step in flight */
-    int step_parity;
-    cudaStream_t aux_stream;        /* the light kernel runs here, beside the heavy contact kernel */
-    cudaEvent_t ev_listed, ev_light; /* fork after the fast kernel / join after the light kernel */
+    int *d_ctl;      /* CTL_TOTAL ints */
+    int *d_list;     /* n ints: contact list of the step in flight */
+    float *d_frames; /* (N,4,22) newest frames, msoc_step_host_frames; allocated on first use */
+    void *d_inject;  /* Arrays::inject, allocated by the first msoc_set_state */
+    cudaStream_t aux_stream[2];        /* the light kernel runs here, beside the heavy contact kernel */
+    cudaEvent_t ev_listed[2], ev_light[2]; /* fork after the fast kernel / join after the light kernel */
+    cudaStream_t pipe_stream;          /* second lane of the chunked host-buffer step */
+    cudaEvent_t ev_pipe_fork, ev_pipe_join;
     void *d_stage; size_t stage_bytes; /* get/set_state staging */
 };
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int BLOCK = WARPS_PER_BLOCK * 32; /* reset kernel */
-constexpr int STEP_BLOCK = 128;             /* step kernel: envs (= threads) per block */
-#ifndef MSOC_STEP_MIN_BLOCKS
-#define MSOC_STEP_MIN_BLOCKS 3
-#endif
-constexpr int STEP_MIN_BLOCKS = MSOC_STEP_MIN_BLOCKS; /* resident blocks per SM the register budget is set for */
 
-/* ------------------------------------------------------------------ coalesced observation rows */
-constexpr int ENV_STRIDE = (SCRATCH_WORDS > 88 ? SCRATCH_WORDS : 88) | 1; /* floats of per-lane scratch in the step kernel: >= 88 (4 new frames) and >= SCRATCH_WORDS; odd: no bank conflicts */
-constexpr int RESET_STRIDE = 89; /* reset kernel: frame staging only */
-
-/* One warp writes the stacked observations of the (up to) 32 envs its lanes own.  Lane l owns env
-   `my_env` (envs need not be consecutive).  An env's 4 rows are 1 056 contiguous, 32-byte aligned bytes =
-   132 float2; row = 33 float2: [frame t-2 | frame t-1 | frame t].  Frames t-2, t-1 come from obs_in
-   shifted by one frame (soccer_env.py:134-137), frame t from shared memory (lane l's 4 frames at
-   s_new + l*ENV_STRIDE); envs in `fresh` (reset / auto-reset, soccer_env.py:92-96) get three copies of the
-   new frame.  Lane j moves float2 j of every row: fully contiguous 8-byte accesses (the +22-float shift is
-   only 8-byte aligned, so float2 is the widest access that keeps loads and stores both contiguous).
-   Safe when obs_out == obs_in: within a batch of rows all loads precede all stores, and one env's rows
-   are only ever touched by the warp that owns it. */
-template <int ENV_STRIDE>
-__device__ __forceinline__ void write_obs_tile(const float2 *in2, float2 *out2, const float *s_new, uint32_t mask,
-                                               uint32_t fresh, int64_t my_env, int lane)
-{
-    const bool lane_hist = lane < 22;                   /* float2 0-21 of a row: history; 22-31: frame t */
-    const int j_lane = lane < 11 ? lane : lane < 22 ? lane - 11 : lane - 22;
-    const float *s_lane = s_new + 2 * j_lane;           /* this lane's float2 of the staged frames */
-#ifndef MSOC_WRITER_ENVS
-#define MSOC_WRITER_ENVS 8
-#endif
-    constexpr int EB = MSOC_WRITER_ENVS; /* envs per batch: 4*EB row loads in flight per lane */
-#pragma unroll 1
-    for (int l0 = 0; l0 < 32; l0 += EB) {
-        const uint32_t mb = (mask >> l0) & ((1u << EB) - 1u);
-        if (mb == 0u) continue;
-        float2 v[EB][4];
-        float2 *po[EB];
-#pragma unroll
-        for (int w = 0; w < EB; w++) {
-            const int64_t ew = __shfl_sync(0xffffffffu, my_env, l0 + w);
-            const float2 *pi = in2 + ew * 132 + lane + 11;
-            po[w] = out2 + ew * 132 + lane;
-            const bool ld = ((mb >> w) & 1u) && lane_hist && !((fresh >> (l0 + w)) & 1u);
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const float *sp = s_lane + (l0 + w) * ENV_STRIDE + a * 22;
-                v[w][a] = make_float2(sp[0], sp[1]);
-                if (ld) v[w][a] = pi[a * 33];
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int w = 0; w < EB; w++) {
-            if (!((mb >> w) & 1u)) continue;
-#pragma unroll
-            for (int a = 0; a < 4; a++) po[w][a * 33] = v[w][a];
-        }
-    }
-    /* last float2 of every row (frame t, floats 20-21): lane l writes its own env's four */
-    if ((mask >> lane) & 1u) {
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const float *sp = s_new + lane * ENV_STRIDE + a * 22 + 20;
-            out2[my_env * 132 + a * 33 + 32] = make_float2(sp[0], sp[1]);
-        }
-    }
-}
+/* ------------------------------------------------------------------ observation blocks */
+constexpr int ENV_STRIDE = SCRATCH_WORDS | 1; /* floats of per-lane solver scratch in the contact kernel; odd: no bank conflicts */
+constexpr int OBS_ENVS = 8;                     /* envs whose observations a warp builds at a time */
+constexpr int BLOCK_WORDS = OBS_ENVS * 4 * OBS;  /* floats of staged observation blocks: 8 x (4 x 66) */
+constexpr int REC_F4 = 7;                        /* float4s of a record that a frame is made of */
+constexpr int RECS_WORDS = OBS_ENVS * 3 * REC_F4 * 4; /* floats of staged records: 8 envs x 3 buffers x 7 float4 */
+constexpr int STAGE_WORDS = BLOCK_WORDS + RECS_WORDS; /* per warp: 8 448 + 2 688 bytes, both 16-byte multiples */
 
 /* ---------------------------------------------------------------------------- the fused step */
 struct StepParams {
     Arrays A;
     SimCfg cfg;
     const float *actions; /* (N,4,3) */
-    const float *obs_in;  /* (N,4,66) */
     float *obs_out;       /* (N,4,66) */
+    float *frames_out;    /* (N,4,22) or null */
     float *reward;        /* (N,2) */
     uint8_t *done;        /* (N) */
     int8_t *goal;         /* (N) */
     int32_t *score;       /* (N,2) or null */
     double *stats;        /* 8 */
-    int *ctl;             /* counters of this step (all start at 0): CTL_* below */
-    int *ctl_other;       /* counters of the next step: zeroed by this one */
-    int *list;            /* N slots: envs that need the contact path -- light from the front, heavy from the back */
+    int *ctl;             /* the handle's control block */
+    int *list;            /* N slots: envs that need the contact path -- light from the front of [e0, e1), heavy from its back */
+    int64_t e0, e1;       /* the envs this launch steps */
     uint64_t global_offset;
     uint32_t flags;
-    int cur;
+    int chunk;            /* -1: a whole step (list counters alternate with the step counter, the contact kernel advances it);
+                             >= 0: one pipeline chunk of a host-buffer step (its own pre-zeroed counters, nobody advances) */
 };
 
 #ifdef MSOC_TIMELINE /* debug build only (tools/timeline.py): when did every batch of every step kernel run? */
@@ -183,10 +136,15 @@ __device__ __forceinline__ void tl_record(int kid, unsigned long long t0) {
 #define MSOC_TL_END(kid) do { } while (0)
 #endif
 /* Per-thread tallies for the per-rollout statistics. */
-struct Tally { int done, goals_b, goals_r, contacts, overflow, envs; float ret; };
+struct Tally { int done, goals_b, goals_r, contacts, overflow, nonfinite; float ret; };
+__device__ __forceinline__ void tally_clear(Tally &T) { T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.nonfinite = 0; T.ret = 0.0f; }
 
-__device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P, int64_t e, Env &E, Work &W, int &load, bool &fresh,
-                                             Tally &T)
+__device__ __forceinline__ int *step_ctl(const StepParams &P, int step) { return P.chunk < 0 ? P.ctl + CTL_WORDS * (step & 1) : P.ctl + CTL_CHUNK0 + CTL_WORDS * P.chunk; }
+
+/* Loads env e (the record of buffer step % 3, or the injected record of a flagged env) and its actions, steps it.  On
+   success (always, except for the contact-free mode, which declines envs that need the contact path) the per-env
+   outputs and the new state are written; the observation follows in obs_tile once the whole warp has stored. */
+__device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P, int step, int64_t e, Work &W, int &load, Tally &T)
 {
     float act[12];
     const float4 *a4 = reinterpret_cast<const float4 *>(P.actions + e * 12);
@@ -194,22 +152,129 @@ __device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P
     act[0] = x0.x; act[1] = x0.y; act[2] = x0.z; act[3] = x0.w;
     act[4] = x1.x; act[5] = x1.y; act[6] = x1.z; act[7] = x1.w;
     act[8] = x2.x; act[9] = x2.y; act[10] = x2.z; act[11] = x2.w;
-    load_env(P.A, e, E);
+    /* soccer_env.py:116-117 raises on non-finite actions; a device-resident caller gets a counter instead (the clip
+       turns NaN into -1) */
+    bool finite = true;
+#pragma unroll
+    for (int k = 0; k < 12; k++) finite = finite && (fabsf(act[k]) <= 3.0e38f);
+    Env E;
+    const float4 *rec = P.A.pose[buf_cur(step)] + e * POSE_F4;
+    if (MODE == MODE_FULL) { /* the only kernel that sees injected states */
+        if (__float_as_uint(rec[7].z) & FLAG_INJECT) rec = P.A.inject + e * POSE_F4;
+    }
+    load_env(P.A, rec, e, E);
     StepOut out;
-    if (!env_step(MODE, E, act, P.cfg, P.A, P.cur, e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
-    store_env(P.A, e, E);
+    if (!env_step(MODE, E, act, P.cfg, P.A, cache_half(step), e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
     reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
     P.done[e] = out.done;
     P.goal[e] = out.goal;
     if (P.score != nullptr) reinterpret_cast<int2 *>(P.score)[e] = make_int2(out.score_b, out.score_r);
-    fresh = out.fresh_episode;
-    T.done += out.done; T.goals_b += out.goal > 0; T.goals_r += out.goal < 0; T.envs += 1;
+    store_env(P.A, buf_next(step), e, E, out.score_dirty);
+    if (out.fresh_episode) { /* a fresh episode has no history but its first frame (soccer_env.py:92-96) */
+        store_env_record(P.A.pose[buf_cur(step)] + e * POSE_F4, E);
+        store_env_record(P.A.pose[buf_prev(step)] + e * POSE_F4, E);
+    }
+    T.nonfinite += finite ? 0 : 1;
+    T.done += out.done; T.goals_b += out.goal > 0; T.goals_r += out.goal < 0;
     T.contacts += out.n_contacts; T.overflow += out.overflow; T.ret += out.finished_return;
     return true;
 }
 
+/* ---- bulk asynchronous copies (the TMA engine, PTX cp.async.bulk): shared memory -> global memory */
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+/* until the engine has READ the shared-memory sources of all committed groups (they may then be overwritten) */
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+/* orders this thread's shared-memory writes before later bulk copies of any thread it then synchronises with */
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* Stacked observations [frame(t-2) | frame(t-1) | frame(t)] (soccer_env.py:130-140) of the warp's envs whose bit is set
+   in `mask` (lane l owns env `my_env`; its new state is stored), eight envs at a time:
+     1. the warp fetches the 8 x 3 records (buffers (step+2)%3, step%3 -- L1/L2 hits, this warp read or prefetched
+        them -- and (step+1)%3, just written by sibling lanes: read from L2) with 16-byte loads, 168 in all, the loads of
+        the next eight envs in flight while the current ones are worked on, and parks them in shared memory;
+     2. lane = (env, agent) rebuilds its agent's three frames and puts them where they belong in the env's 4 x 66 block;
+     3. the blocks leave as bulk asynchronous copies, one per env (1 056 contiguous, 32-byte aligned bytes = 33 whole
+        sectors; nothing is ever read back or written twice).
+   frames_out (or null): the newest frames once more, compact (N,4,22), for the host path. */
+struct RecLoad { float4 v[6]; };
+__device__ __forceinline__ void obs_fetch(const Arrays &A, int step, uint32_t mask, int g, int64_t my_env, int lane, RecLoad &R)
+{
+    const uint32_t m8 = (mask >> (8 * g)) & 0xffu;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        const int sl = r * 32 + lane;            /* slot in [buffer][env][float4] order, 168 used */
+        const int k = sl / (OBS_ENVS * REC_F4), rem = sl - k * (OBS_ENVS * REC_F4);
+        const int e8 = rem / REC_F4, f = rem - e8 * REC_F4;
+        const int64_t env = __shfl_sync(0xffffffffu, my_env, (8 * g + e8) & 31);
+        R.v[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (sl < 3 * OBS_ENVS * REC_F4 && ((m8 >> e8) & 1u)) {
+            const int b = k == 0 ? buf_prev(step) : k == 1 ? buf_cur(step) : buf_next(step);
+            const float4 *p = A.pose[b] + env * POSE_F4 + f;
+            R.v[r] = k == 2 ? __ldcg(p) : *p;
+        }
+    }
+}
+__device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, float *obs_out, float *frames_out, int step, float *s_stage,
+                                         uint32_t mask, int64_t my_env, int lane)
+{
+    const int a = lane & 3, el = lane >> 2;
+    float4 *recs4 = reinterpret_cast<float4 *>(s_stage + BLOCK_WORDS);
+    float2 *mine = reinterpret_cast<float2 *>(s_stage) + lane * 33; /* row (el, a) of the staged blocks */
+    __syncwarp(); /* the siblings' stores of the new records are ordered before the loads below */
+    int g = __ffs((int)((mask & 0xffu ? 1u : 0u) | (mask & 0xff00u ? 2u : 0u) | (mask & 0xff0000u ? 4u : 0u) | (mask & 0xff000000u ? 8u : 0u))) - 1;
+    RecLoad R;
+    obs_fetch(A, step, mask, g, my_env, lane, R);
+#pragma unroll 1
+    while (true) {
+        const uint32_t m8 = (mask >> (8 * g)) & 0xffu;
+        /* the staging areas are free: every lane has waited for its own bulk copies, then the warp synchronised */
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+            if (r * 32 + lane < 3 * OBS_ENVS * REC_F4) recs4[r * 32 + lane] = R.v[r];
+        __syncwarp();
+        /* next group with work, its loads in flight from here on */
+        int gn = g + 1;
+        while (gn < 4 && ((mask >> (8 * gn)) & 0xffu) == 0u) gn++;
+        if (gn < 4) obs_fetch(A, step, mask, gn, my_env, lane, R);
+        const int64_t env = __shfl_sync(0xffffffffu, my_env, 8 * g + el);
+        if ((m8 >> el) & 1u) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float o[22];
+                frame_of_record(recs4 + (k * OBS_ENVS + el) * REC_F4, a, false, cfg, o);
+#pragma unroll
+                for (int i = 0; i < 11; i++) mine[k * 11 + i] = make_float2(o[2 * i], o[2 * i + 1]);
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (a == 0 && ((m8 >> el) & 1u)) /* one lane per env */
+            bulk_store(obs_out + env * (4 * OBS), s_stage + el * (4 * OBS), 4 * OBS * sizeof(float));
+        bulk_commit();
+        if (frames_out != nullptr) {
+            float2 *fr2 = reinterpret_cast<float2 *>(frames_out);
+            const float2 *stage2 = reinterpret_cast<const float2 *>(s_stage);
+#pragma unroll
+            for (int it = 0; it < 11; it++) { /* 8 x 4 x 11 = 352 float2: the third frame of every row */
+                const int idx = it * 32 + lane;
+                const int row = idx / 11, j = idx - row * 11;
+                const int64_t env2 = __shfl_sync(0xffffffffu, my_env, 8 * g + (row >> 2));
+                if ((m8 >> (row >> 2)) & 1u) fr2[env2 * 44 + (row & 3) * 11 + j] = stage2[row * 33 + 22 + j];
+            }
+        }
+        bulk_wait_read();
+        __syncwarp();
+        if (gn >= 4) break;
+        g = gn;
+    }
+}
+
 /* The fused step is three launches, each tuned for its share of the work.
-   msoc_step_fast_kernel     streams over ALL envs, thread t of block b steps env b*128 + t in contact-free
+   msoc_step_fast_kernel     streams over ALL envs, thread t of block b steps env e0 + b*128 + t in contact-free
                              mode and its warp writes the observation rows.  No contact code is compiled into
                              it: few registers, small shared memory, small instruction footprint -> many
                              resident warps to hide the HBM latency.  Envs whose broad phase finds a candidate
@@ -225,15 +290,17 @@ __device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P
                              writes the rows.
    The divergent, latency-bound contact work therefore always runs on full warps of similar work, and each
    kind of work gets the register / shared-memory budget (hence the occupancy) that suits it.  The two contact
-   kernels only depend on the fast kernel's lists and are launched on two streams (msoc_step). */
-enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
+   kernels only depend on the fast kernel's lists and are launched on two streams (msoc_step).
 
-constexpr int FAST_STRIDE = 89; /* floats of per-lane frame staging in the fast kernel (88, odd: no bank conflicts) */
+   Which half of the ping-pong state is current is a step counter in DEVICE memory (so a captured CUDA graph of any
+   number of steps replays correctly): the fast kernel reads ctl[CTL_STEP_FAST] and copies it to ctl[CTL_STEP_CONTACT]
+   for the two contact kernels of the same step; the contact kernel, which only starts when the fast kernel is complete
+   and is complete before the next fast kernel starts, writes the incremented counter back. */
 #ifndef MSOC_FAST_BLOCK
 #define MSOC_FAST_BLOCK 128
 #endif
 constexpr int FAST_BLOCK = MSOC_FAST_BLOCK; /* envs (= threads) per block of the fast kernel */
-constexpr size_t FAST_SMEM_BYTES = (size_t)FAST_BLOCK * FAST_STRIDE * sizeof(float);
+constexpr size_t FAST_SMEM_BYTES = (size_t)(FAST_BLOCK / 32) * STAGE_WORDS * sizeof(float);
 #ifndef MSOC_FAST_MIN_BLOCKS
 #define MSOC_FAST_MIN_BLOCKS 4
 #endif
@@ -254,73 +321,81 @@ __device__ __forceinline__ void push_warp(int *tail, bool want, int env, int lan
 /* warp reduce of the per-rollout statistics (marl-soccer.ipynb:411-429), one atomic per warp and counter */
 __device__ __forceinline__ void flush_tally(const Tally &T, double *stats, int lane)
 {
-    int nd = T.done, gb = T.goals_b, gr = T.goals_r, nc = T.contacts, ov = T.overflow, na = T.envs;
+    int nd = T.done, gb = T.goals_b, gr = T.goals_r, nc = T.contacts, ov = T.overflow, nf = T.nonfinite;
     float ret = T.ret;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         nd += __shfl_xor_sync(0xffffffffu, nd, o); gb += __shfl_xor_sync(0xffffffffu, gb, o);
         gr += __shfl_xor_sync(0xffffffffu, gr, o); nc += __shfl_xor_sync(0xffffffffu, nc, o);
-        ov += __shfl_xor_sync(0xffffffffu, ov, o); na += __shfl_xor_sync(0xffffffffu, na, o);
+        ov += __shfl_xor_sync(0xffffffffu, ov, o);
+        nf += __shfl_xor_sync(0xffffffffu, nf, o);
         ret += __shfl_xor_sync(0xffffffffu, ret, o);
     }
     if (lane == 0) {
         if (nd) { atomicAdd(stats + 0, (double)nd); atomicAdd(stats + 1, (double)ret); }
         if (gb) atomicAdd(stats + 2, (double)gb);
         if (gr) atomicAdd(stats + 3, (double)gr);
-        if (na) atomicAdd(stats + 4, (double)na);
         if (nc) atomicAdd(stats + 5, (double)nc);
         if (ov) atomicAdd(stats + 6, (double)ov);
+        if (nf) atomicAdd(stats + 7, (double)nf);
     }
 }
 
 __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fast_kernel(const __grid_constant__ StepParams P)
 {
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(16) float s_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
-    if (blockIdx.x == 0 && tid < CTL_WORDS) P.ctl_other[tid] = 0;
+    float *s_warp = s_dyn + warp * STAGE_WORDS;
+    const int step = P.ctl[CTL_STEP_FAST];
+    int *ctl = step_ctl(P, step);
+    if (blockIdx.x == 0) {
+        if (P.chunk < 0 && tid < CTL_WORDS) P.ctl[CTL_WORDS * ((step & 1) ^ 1) + tid] = 0; /* the next step's list counters */
+        if (tid == 0) {
+            P.ctl[CTL_STEP_CONTACT] = step;
+            atomicAdd(P.stats + 4, (double)(P.e1 - P.e0)); /* every env of the range is stepped by one of the three kernels */
+        }
+    }
     MSOC_TL_BEGIN();
-    const int64_t my_env = (int64_t)blockIdx.x * FAST_BLOCK + tid;
-    const bool have = my_env < P.A.n;
-    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    const int64_t my_env = P.e0 + (int64_t)blockIdx.x * FAST_BLOCK + tid;
+    const bool have = my_env < P.e1;
+    Tally T; tally_clear(T);
     Work W; /* never touched in contact-free mode */
     W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
-    bool fresh = false, ok = false;
+    bool ok = false;
     int load = 0;
-    {
-        Env E;
-        if (have) ok = step_one_env(MODE_FAST, P, my_env, E, W, load, fresh, T);
-        if (ok) make_frames<22>(E, P.cfg, s_warp + lane * FAST_STRIDE);
+    if (have) {
+        /* the oldest of the three records the observation is rebuilt from is not needed by the step: start pulling it */
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A.pose[buf_prev(step)] + my_env * POSE_F4));
+        ok = step_one_env(MODE_FAST, P, step, my_env, W, load, T);
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
-    __syncwarp();
-    if (mask) write_obs_tile<FAST_STRIDE>(reinterpret_cast<const float2 *>(P.obs_in), reinterpret_cast<float2 *>(P.obs_out), s_warp, mask,
-                                          fmask, my_env, lane);
+    if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
     const bool declined = have && !ok;
-    push_warp(P.ctl + CTL_LIGHT, declined && load == 0, (int)my_env, lane, [&](int i) { return P.list + i; });
-    push_warp(P.ctl + CTL_HEAVY, declined && load != 0, (int)my_env, lane, [&](int i) { return P.list + (P.A.n - 1 - i); });
+    push_warp(ctl + CTL_LIGHT, declined && load == 0, (int)my_env, lane, [&](int i) { return P.list + (P.e0 + i); });
+    push_warp(ctl + CTL_HEAVY, declined && load != 0, (int)my_env, lane, [&](int i) { return P.list + (P.e1 - 1 - i); });
     flush_tally(T, P.stats, lane);
     if ((blockIdx.x & 15) == 0 && warp == 0) MSOC_TL_END(0);
 }
 
 /* Light envs (exactly one agent x wall candidate pair, ~82 % of the contact envs): thread t of a batch steps
    one listed env with the register-only single-body solver of step_core.cuh (MODE_LIGHT).  Like the fast
-   kernel it needs no solver scratch: shared memory only stages the frames. */
+   kernel it needs no solver scratch: shared memory only stages the observation blocks. */
 #ifndef MSOC_LIGHT_BLOCK
 #define MSOC_LIGHT_BLOCK 64 /* small blocks: they slip into an SM as soon as one heavy block has left it */
 #endif
 constexpr int LIGHT_BLOCK = MSOC_LIGHT_BLOCK;
 constexpr int LIGHT_MIN_BLOCKS = 512 / LIGHT_BLOCK; /* 128 registers per thread */
-constexpr size_t LIGHT_SMEM_BYTES = (size_t)LIGHT_BLOCK * FAST_STRIDE * sizeof(float);
+constexpr size_t LIGHT_SMEM_BYTES = (size_t)(LIGHT_BLOCK / 32) * STAGE_WORDS * sizeof(float);
 __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light_kernel(const __grid_constant__ StepParams P)
 {
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(16) float s_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *s_warp = s_dyn + warp * 32 * FAST_STRIDE;
-    const int n_light = P.ctl[CTL_LIGHT]; /* final: the fast kernel has finished */
+    float *s_warp = s_dyn + warp * STAGE_WORDS;
+    const int step = P.ctl[CTL_STEP_CONTACT];
+    int *ctl = step_ctl(P, step);
+    const int n_light = ctl[CTL_LIGHT]; /* final: the fast kernel has finished */
     const int batches = (n_light + 31) / 32;
-    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    Tally T; tally_clear(T);
     Work W; /* never touched in light mode */
     W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
 #pragma unroll 1
@@ -328,60 +403,57 @@ __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light
         /* every warp takes its own batches of 32 envs, handed out dynamically: this kernel runs beside the heavy
            contact kernel and its blocks start whenever an SM has room for them */
         int b = 0;
-        if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_LIGHT, 1);
+        if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_LIGHT, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= batches) break;
         const int idx = b * 32 + lane;
         const bool have = idx < n_light;
-        const int64_t my_env = have ? (int64_t)P.list[idx] : 0;
+        const int64_t my_env = have ? (int64_t)P.list[P.e0 + idx] : 0;
         MSOC_TL_BEGIN();
-        bool fresh = false, ok = false;
+        bool ok = false;
         int load = 0;
-        {
-            Env E;
-            if (have) ok = step_one_env(MODE_LIGHT, P, my_env, E, W, load, fresh, T);
-            if (ok) make_frames<22>(E, P.cfg, s_warp + lane * FAST_STRIDE);
+        if (have) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A.pose[buf_prev(step)] + my_env * POSE_F4));
+            ok = step_one_env(MODE_LIGHT, P, step, my_env, W, load, T);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-        const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
-        __syncwarp();
-        if (mask) write_obs_tile<FAST_STRIDE>(reinterpret_cast<const float2 *>(P.obs_in), reinterpret_cast<float2 *>(P.obs_out), s_warp,
-                                              mask, fmask, my_env, lane);
-        __syncwarp(); /* the staging area is rewritten by the next batch */
+        if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
         MSOC_TL_END(1);
     }
     flush_tally(T, P.stats, lane);
 }
 
-/* Per-warp scratch of 32 x ENV_STRIDE floats, time-multiplexed: during the contact solve it holds the
-   lanes' solver bodies (30 fields, field-major with stride 32: conflict-free), the warp's pool of
-   32 x CON_FAST contact records (15 fields, field-major; an env takes as many records as it has contacts),
-   the parked poses and the preloaded arbiter cache entries; afterwards the lanes' four new observation
-   frames (lane-major, stride ENV_STRIDE). */
-static_assert(SCRATCH_WORDS <= ENV_STRIDE && 88 <= ENV_STRIDE, "per-lane scratch too small");
+/* Per-warp scratch of 32 x ENV_STRIDE floats: during the contact solve it holds the lanes' solver bodies (30 fields,
+   field-major with stride 32: conflict-free), the warp's pool of 32 x CON_FAST contact records (15 fields, field-major;
+   an env takes as many records as it has contacts), the parked poses and the preloaded arbiter cache entries;
+   afterwards the staged observation blocks. */
+static_assert(STAGE_WORDS <= 32 * ENV_STRIDE, "the observation staging must fit the per-warp solver scratch");
 #ifndef MSOC_HEAVY_BLOCK
-#define MSOC_HEAVY_BLOCK 64 /* threads per block of the heavy contact kernel: one warp, so that an SM's registers and shared
-                               memory are handed to the light kernel warp by warp as the heavy batches finish */
+#define MSOC_HEAVY_BLOCK 64 /* threads per block of the heavy contact kernel: small, so that an SM's registers and shared
+                               memory are handed to the light kernel block by block as the heavy batches finish */
 #endif
 constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
 #ifndef MSOC_HEAVY_MIN_BLOCKS
-#define MSOC_HEAVY_MIN_BLOCKS 5 /* register cap 204: ptxas settles on 168 without spills (with 6 it spills 48 B); 6 blocks are resident all the same */
+#define MSOC_HEAVY_MIN_BLOCKS 5 /* register cap 204 */
 #endif
 constexpr int HEAVY_MIN_BLOCKS = MSOC_HEAVY_MIN_BLOCKS;
-constexpr size_t STEP_SMEM_BYTES = (size_t)HEAVY_BLOCK * ENV_STRIDE * sizeof(float);
+constexpr int HEAVY_WARP_WORDS = (32 * ENV_STRIDE + 3) & ~3; /* 16-byte aligned per-warp scratch */
+constexpr size_t STEP_SMEM_BYTES = (size_t)(HEAVY_BLOCK / 32) * HEAVY_WARP_WORDS * sizeof(float);
 
 __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
 {
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(16) float s_dyn[];
     __shared__ int s_pool_count[HEAVY_BLOCK / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *s_warp = s_dyn + warp * 32 * ENV_STRIDE;
-    const int n_heavy = P.ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
+    float *s_warp = s_dyn + warp * HEAVY_WARP_WORDS;
+    const int step = P.ctl[CTL_STEP_CONTACT];
+    int *ctl = step_ctl(P, step);
+    /* this step's fast kernel is complete and the next one starts after this kernel: advance the step counter */
+    if (P.chunk < 0 && blockIdx.x == 0 && tid == 0) P.ctl[CTL_STEP_FAST] = (step + 1) % 6;
+    const int n_heavy = ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
     const int heavy_batches = (n_heavy + 31) / 32;
-    const float2 *in2 = reinterpret_cast<const float2 *>(P.obs_in);
-    float2 *out2 = reinterpret_cast<float2 *>(P.obs_out);
 
-    Tally T; T.done = T.goals_b = T.goals_r = T.contacts = T.overflow = T.envs = 0; T.ret = 0.0f;
+    Tally T; tally_clear(T);
     float ovf_store[MAXC - CON_FAST][CON_FIELDS]; /* local memory, touched only by envs with more than CON_FAST contacts */
     Work W;
     W.ovf = ovf_store;
@@ -395,33 +467,32 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         /* every WARP takes its own batches of 32 envs, handed out dynamically (the scratch is per warp, so the warps
            of a block never wait for each other; the batches differ a lot in length) */
         int b = 0;
-        if (lane == 0) b = atomicAdd(P.ctl + CTL_NEXT_HEAVY, 1);
+        if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_HEAVY, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= heavy_batches) break;
         const int idx = b * 32 + lane;
         const bool have = idx < n_heavy;
         int64_t my_env = 0;
-        if (have) my_env = (int64_t)P.list[P.A.n - 1 - idx];
+        if (have) my_env = (int64_t)P.list[P.e1 - 1 - idx];
         MSOC_TL_BEGIN();
-        bool fresh = false, ok = false;
+        bool ok = false;
         int load = 0;
         if (lane == 0) *W.pool_count = 0; /* the warp's contact pool is empty */
         __syncwarp();
-        {
-            Env E;
-            if (have) ok = step_one_env(MODE_FULL, P, my_env, E, W, load, fresh, T);
-            __syncwarp(); /* the solver scratch of every lane is dead: reuse it for the frames */
-            if (ok) make_frames<22>(E, P.cfg, s_warp + lane * ENV_STRIDE);
+        if (have) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A.pose[buf_prev(step)] + my_env * POSE_F4));
+            ok = step_one_env(MODE_FULL, P, step, my_env, W, load, T);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-        const uint32_t fmask = __ballot_sync(0xffffffffu, ok && fresh);
-        __syncwarp();
-        if (mask) write_obs_tile<ENV_STRIDE>(in2, out2, s_warp, mask, fmask, my_env, lane);
-        __syncwarp();
+        /* (obs_tile starts with a __syncwarp: the solver scratch of every lane is dead before it is reused) */
+        if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
         MSOC_TL_END(2);
     }
     flush_tally(T, P.stats, lane);
 }
+
+/* advances the step counter after a chunked host-buffer step (whose contact kernels do not) */
+__global__ void msoc_advance_kernel(int *ctl) { ctl[CTL_STEP_FAST] = (ctl[CTL_STEP_FAST] + 1) % 6; }
 
 /* ------------------------------------------------------------------------------------- reset */
 struct ResetParams {
@@ -429,17 +500,19 @@ struct ResetParams {
     SimCfg cfg;
     const uint8_t *mask; /* N or null */
     float *obs_out;      /* (N,4,66) or null */
+    const int *ctl;
     uint64_t global_offset, seed;
-    int mode, has_seed, cur;
+    int mode, has_seed;
 };
 
 __global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant__ ResetParams P)
 {
-    __shared__ float s_frames[WARPS_PER_BLOCK][32 * RESET_STRIDE];
+    __shared__ __align__(16) float s_stage[WARPS_PER_BLOCK][STAGE_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t block_base = (int64_t)blockIdx.x * BLOCK;
     const int64_t e = block_base + threadIdx.x;
     if (block_base + warp * 32 >= P.A.n) return;
+    const int step = P.ctl[CTL_STEP_FAST];
     const bool doit = (e < P.A.n) && (P.mask == nullptr || P.mask[e] != 0);
     if (doit) {
         const uint64_t gidx = P.global_offset + (uint64_t)e;
@@ -449,25 +522,51 @@ __global__ void __launch_bounds__(BLOCK) msoc_reset_kernel(const __grid_constant
         Env E;
         env_full_reset(E, P.mode, seed, gidx, sc);
         P.A.spawn_count[e] = sc;
-        store_env(P.A, e, E);
-        make_frames<22>(E, P.cfg, &s_frames[warp][lane * RESET_STRIDE]);
+        /* all three buffers: the observation history of a fresh episode is its first frame (soccer_env.py:92-96).
+           The state the next step starts from is buffer step % 3. */
+        store_env(P.A, buf_cur(step), e, E, true);
+        store_env_record(P.A.pose[buf_prev(step)] + e * POSE_F4, E);
+        store_env_record(P.A.pose[buf_next(step)] + e * POSE_F4, E);
     }
     const uint32_t m = __ballot_sync(0xffffffffu, doit);
-    __syncwarp();
-    if (P.obs_out != nullptr && m != 0u) {
-        float2 *o2 = reinterpret_cast<float2 *>(P.obs_out);
-        write_obs_tile<RESET_STRIDE>(o2, o2, s_frames[warp], m, m, e, lane);
-    }
+    if (P.obs_out != nullptr && m != 0u) obs_tile(P.A, P.cfg, P.obs_out, nullptr, step, s_stage[warp], m, e, lane);
 }
 
 /* -------------------------------------------------------------------- state inject / extract */
-__global__ void msoc_get_state_kernel(Arrays A, int cur, const int64_t *idx, int64_t n, msoc_env_state *out)
+__device__ __forceinline__ void hist_to_record(const msoc_env_state &S, int k, float4 *r)
+{
+    Pose Q;
+    for (int i = 0; i < 5; i++) { Q.px[i] = S.hist_pos[k][i][0]; Q.py[i] = S.hist_pos[k][i][1]; }
+    for (int i = 0; i < 4; i++) { Q.vx[i] = S.hist_vel[k][i][0]; Q.vy[i] = S.hist_vel[k][i][1]; Q.ang[i] = S.hist_ang[k][i]; Q.w[i] = S.hist_angvel[k][i]; }
+    pose_pack(Q, 0.0f, 0.0f, r);
+}
+__device__ __forceinline__ void record_to_hist(const float4 *r, msoc_env_state &S, int k)
+{
+    Pose Q; pose_unpack(r, Q);
+    for (int i = 0; i < 5; i++) { S.hist_pos[k][i][0] = Q.px[i]; S.hist_pos[k][i][1] = Q.py[i]; }
+    for (int i = 0; i < 4; i++) { S.hist_vel[k][i][0] = Q.vx[i]; S.hist_vel[k][i][1] = Q.vy[i]; S.hist_ang[k][i] = Q.ang[i]; S.hist_angvel[k][i] = Q.w[i]; }
+}
+/* same pose?  (bit patterns of the 26 floats a frame is made of; the ball velocity in r[4].zw is not part of it) */
+__device__ __forceinline__ bool same_pose(const float4 *a, const float4 *b)
+{
+    bool same = true;
+    for (int i = 0; i < 7; i++) {
+        same = same && __float_as_uint(a[i].x) == __float_as_uint(b[i].x) && __float_as_uint(a[i].y) == __float_as_uint(b[i].y);
+        if (i != 4) same = same && __float_as_uint(a[i].z) == __float_as_uint(b[i].z) && __float_as_uint(a[i].w) == __float_as_uint(b[i].w);
+    }
+    return same;
+}
+
+__global__ void msoc_get_state_kernel(Arrays A, const int *ctl, const int64_t *idx, int64_t n, msoc_env_state *out)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    const int step = ctl[CTL_STEP_FAST];
     const int64_t e = idx[t];
+    const float4 *rec = A.pose[buf_cur(step)] + e * POSE_F4;
+    const bool injected = (__float_as_uint(rec[7].z) & FLAG_INJECT) != 0u && A.inject != nullptr;
     Env E;
-    load_env(A, e, E);
+    load_env(A, injected ? A.inject + e * POSE_F4 : rec, e, E);
     msoc_env_state S;
     memset(&S, 0, sizeof S);
     for (int i = 0; i < 5; i++) {
@@ -481,16 +580,20 @@ __global__ void msoc_get_state_kernel(Arrays A, int cur, const int64_t *idx, int
     const uint32_t cnt = E.flags & FLAG_CACHE_MASK;
     S.cache_count = cnt;
     for (uint32_t j = 0; j < cnt; j++) {
-        const uint32_t *c = A.cache[cur] + cache_slot(e, (int)j);
+        const uint32_t *c = A.cache[cache_half(step)] + cache_slot(e, (int)j);
         S.cache_info[j] = c[0]; S.cache_jn[j] = __uint_as_float(c[1]); S.cache_jt[j] = __uint_as_float(c[2]);
     }
+    S.hist_valid = 1u;
+    record_to_hist(A.pose[buf_prev(step)] + e * POSE_F4, S, 0);
+    record_to_hist(rec, S, 1);
     out[t] = S;
 }
 
-__global__ void msoc_set_state_kernel(Arrays A, int cur, const int64_t *idx, int64_t n, const msoc_env_state *in)
+__global__ void msoc_set_state_kernel(Arrays A, const int *ctl, const int64_t *idx, int64_t n, const msoc_env_state *in)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    const int step = ctl[CTL_STEP_FAST];
     const int64_t e = idx[t];
     const msoc_env_state &S = in[t];
     Env E;
@@ -504,10 +607,42 @@ __global__ void msoc_set_state_kernel(Arrays A, int cur, const int64_t *idx, int
     E.flags = cnt | (((uint32_t)S.mode & 3u) << FLAG_MODE_SHIFT);
     A.spawn_count[e] = S.spawn_count; A.seed[e] = S.seed;
     for (uint32_t j = 0; j < cnt; j++) {
-        uint32_t *c = A.cache[cur] + cache_slot(e, (int)j);
+        uint32_t *c = A.cache[cache_half(step)] + cache_slot(e, (int)j);
         c[0] = S.cache_info[j]; c[1] = __float_as_uint(S.cache_jn[j]); c[2] = __float_as_uint(S.cache_jt[j]);
     }
-    store_env(A, e, E);
+    /* The observation history.  The frames already emitted stay what they were (the reference's deque is not touched by
+       a poke of the bodies): the current record keeps the pose behind the newest of them and the injected state goes to
+       Arrays::inject -- unless the two poses are the same bits.  With hist_valid the caller supplies both history poses
+       (checkpoint restore, parity injection). */
+    float4 *rec = A.pose[buf_cur(step)] + e * POSE_F4;
+    float4 newp[7], prev[7];
+    { Pose Q; pose_of(E, Q); pose_pack(Q, 0.0f, 0.0f, newp); }
+    if (S.hist_valid) {
+        float4 h0[7];
+        hist_to_record(S, 0, h0);
+        for (int i = 0; i < 7; i++) A.pose[buf_prev(step)][e * POSE_F4 + i] = h0[i];
+        hist_to_record(S, 1, prev);
+    } else {
+        for (int i = 0; i < 7; i++) prev[i] = rec[i];
+    }
+    store_env_bias(A, e, E);
+    A.score[e] = make_int2(E.score_b, E.score_r);
+    if (same_pose(prev, newp)) {
+        store_env_record(rec, E);
+    } else {
+        store_env_record(A.inject + e * POSE_F4, E);
+        for (int i = 0; i < 7; i++) rec[i] = prev[i];
+        rec[7] = make_float4(0.0f, __uint_as_float((uint32_t)E.steps), __uint_as_float(FLAG_INJECT), 0.0f);
+    }
+}
+
+/* rows of the internal observation buffer of a list of envs, packed */
+__global__ void msoc_gather_obs_kernel(const float *obs, const int64_t *idx, int64_t n, float *out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 4 * OBS) return;
+    const int64_t k = t / (4 * OBS);
+    out[t] = obs[idx[k] * 4 * OBS + (t - k * 4 * OBS)];
 }
 
 __global__ void msoc_init_kernel(Arrays A, uint64_t seed)
@@ -542,14 +677,17 @@ static void fill_cfg(const msoc_config *c, SimCfg &s)
     s.goal_reward = c->goal_scored_reward; s.conceded_penalty = c->goal_conceded_penalty;
     s.alive_penalty = c->alive_penalty; s.score_diff_mult = c->score_difference_multiplier;
     s.max_steps = c->max_steps; s.pad = 0;
+    cfg_derive(s);
 }
 
 int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, uint64_t seed, float *d_obs_out, void *stream);
+int msoc_destroy(msoc_handle *h);
 
 int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t seed, uint64_t global_env_offset,
                 msoc_handle **out)
 {
     if (!cfg || !out || n_envs <= 0) return fail(MSOC_ERR_INVALID, "msoc_create: bad argument");
+    if (n_envs > 0x7fffffff) return fail(MSOC_ERR_INVALID, "msoc_create: at most 2^31 - 1 envs per handle");
     if (!(cfg->agent_mass > 0.0f) || !(cfg->ball_mass > 0.0f) || !(cfg->agent_moment > 0.0f) || !(cfg->ball_moment > 0.0f))
         return fail(MSOC_ERR_INVALID, "msoc_create: masses and moments must be positive");
     int ndev = 0;
@@ -561,43 +699,46 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
 
     msoc_handle *h = new msoc_handle();
     memset(h, 0, sizeof *h);
-    h->device = device; h->n = n_envs; h->global_offset = global_env_offset; h->cur = 0;
+    h->device = device; h->n = n_envs; h->global_offset = global_env_offset;
     fill_cfg(cfg, h->cfg);
+    /* every failure below goes through msoc_destroy, which releases whatever exists so far */
+    auto bail = [&](int code, const char *what, cudaError_t e) { msoc_destroy(h); return fail(code, what, e); };
 
     const size_t n = (size_t)n_envs;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-    const size_t o_bodies = take(n * 5 * sizeof(float4)), o_misc = take(n * 4 * sizeof(float4));
+    size_t o_pose[3], o_cache[2];
+    for (int k = 0; k < 3; k++) o_pose[k] = take(n * POSE_F4 * sizeof(float4));
+    const size_t o_iscore = take(n * sizeof(int2));
     const size_t o_bias = take(n * 4 * sizeof(float4));
     const size_t o_seed = take(n * sizeof(uint64_t)), o_sc = take(n * sizeof(uint32_t));
-    size_t o_cache[2];
     for (int k = 0; k < 2; k++) o_cache[k] = take(n * MAX_CACHE * 3 * sizeof(uint32_t));
     const size_t o_obs = take(n * 4 * OBS * sizeof(float)), o_act = take(n * 12 * sizeof(float));
     const size_t o_rew = take(n * 2 * sizeof(float)), o_done = take(n), o_goal = take(n), o_mask = take(n);
     const size_t o_score = take(n * 2 * sizeof(int32_t));
     const size_t o_stats = take(8 * sizeof(double));
-    const size_t o_tile = take(2 * 4 * sizeof(int));
+    const size_t o_ctl = take(CTL_TOTAL * sizeof(int));
     const size_t o_list = take(n * sizeof(int));
     const size_t total = off;
 
     ce = cudaMalloc(&h->slab, total);
-    if (ce != cudaSuccess) { delete h; return fail(MSOC_ERR_ALLOC, "msoc_create: cudaMalloc", ce); }
+    if (ce != cudaSuccess) return bail(MSOC_ERR_ALLOC, "msoc_create: cudaMalloc", ce);
     ce = cudaMemset(h->slab, 0, total);
-    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: cudaMemset", ce); }
+    if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: cudaMemset", ce);
     char *base = (char *)h->slab;
     Arrays &A = h->A;
     A.n = n_envs;
-    A.bodies = (float4 *)(base + o_bodies); A.misc = (float4 *)(base + o_misc);
+    for (int k = 0; k < 3; k++) A.pose[k] = (float4 *)(base + o_pose[k]);
+    for (int k = 0; k < 2; k++) A.cache[k] = (uint32_t *)(base + o_cache[k]);
+    A.score = (int2 *)(base + o_iscore);
     A.bias = (float4 *)(base + o_bias);
+    A.inject = nullptr;
     A.seed = (uint64_t *)(base + o_seed); A.spawn_count = (uint32_t *)(base + o_sc);
-    for (int k = 0; k < 2; k++) {
-        A.cache[k] = (uint32_t *)(base + o_cache[k]);
-    }
     h->d_obs = (float *)(base + o_obs); h->d_act = (float *)(base + o_act); h->d_rew = (float *)(base + o_rew);
     h->d_done = (uint8_t *)(base + o_done); h->d_goal = (int8_t *)(base + o_goal); h->d_mask = (uint8_t *)(base + o_mask);
     h->d_score = (int32_t *)(base + o_score);
     h->d_stats = (double *)(base + o_stats);
-    h->d_ctl = (int *)(base + o_tile);
+    h->d_ctl = (int *)(base + o_ctl);
     h->d_list = (int *)(base + o_list);
 
     ce = cudaFuncSetAttribute(msoc_step_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
@@ -607,23 +748,26 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
         ce = cudaFuncSetAttribute(msoc_step_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
     if (ce == cudaSuccess)
         ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, LIGHT_BLOCK, LIGHT_SMEM_BYTES);
-    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce); }
+    if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);
-    if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) {
-        cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
+    if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) return bail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
+    for (int k = 0; k < 2 && ce == cudaSuccess; k++) {
+        ce = cudaStreamCreateWithFlags(&h->aux_stream[k], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_listed[k], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_light[k], cudaEventDisableTiming);
     }
-    ce = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_listed, cudaEventDisableTiming);
-    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_light, cudaEventDisableTiming);
-    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: stream/event", ce); }
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->pipe_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_pipe_fork, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_pipe_join, cudaEventDisableTiming);
+    if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: stream/event", ce);
     msoc_init_kernel<<<(unsigned)((n_envs + 255) / 256), 256>>>(A, seed);
     g_launches++;
     /* Game.__init__ -> setup_field -> reset(): first spawn in the default random mode */
     int rc = msoc_reset(h, nullptr, MSOC_MODE_RANDOM, 0, 0, h->d_obs, nullptr);
-    if (rc != MSOC_OK) { cudaFree(h->slab); delete h; return rc; }
+    if (rc != MSOC_OK) { msoc_destroy(h); return rc; }
     ce = cudaDeviceSynchronize();
-    if (ce != cudaSuccess) { cudaFree(h->slab); delete h; return fail(MSOC_ERR_CUDA, "msoc_create: init", ce); }
+    if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: init", ce);
     *out = h;
     return MSOC_OK;
 }
@@ -634,10 +778,17 @@ int msoc_destroy(msoc_handle *h)
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
     if (h->d_stage) cudaFree(h->d_stage);
-    if (h->ev_listed) cudaEventDestroy(h->ev_listed);
-    if (h->ev_light) cudaEventDestroy(h->ev_light);
-    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
-    cudaFree(h->slab);
+    if (h->d_frames) cudaFree(h->d_frames);
+    if (h->d_inject) cudaFree(h->d_inject);
+    for (int k = 0; k < 2; k++) {
+        if (h->ev_listed[k]) cudaEventDestroy(h->ev_listed[k]);
+        if (h->ev_light[k]) cudaEventDestroy(h->ev_light[k]);
+        if (h->aux_stream[k]) cudaStreamDestroy(h->aux_stream[k]);
+    }
+    if (h->ev_pipe_fork) cudaEventDestroy(h->ev_pipe_fork);
+    if (h->ev_pipe_join) cudaEventDestroy(h->ev_pipe_join);
+    if (h->pipe_stream) cudaStreamDestroy(h->pipe_stream);
+    if (h->slab) cudaFree(h->slab);
     delete h;
     return MSOC_OK;
 }
@@ -648,71 +799,134 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
     if (mode < 0 || mode > 2) return fail(MSOC_ERR_INVALID, "msoc_reset: bad mode");
     DeviceGuard guard(h->device);
     ResetParams P;
-    P.A = h->A; P.cfg = h->cfg; P.mask = d_mask; P.obs_out = d_obs_out;
-    P.global_offset = h->global_offset; P.seed = seed; P.mode = mode; P.has_seed = has_seed; P.cur = h->cur;
+    P.A = h->A; P.cfg = h->cfg; P.mask = d_mask; P.obs_out = d_obs_out; P.ctl = h->d_ctl;
+    P.global_offset = h->global_offset; P.seed = seed; P.mode = mode; P.has_seed = has_seed;
     msoc_reset_kernel<<<grid_for(h->n), BLOCK, 0, (cudaStream_t)stream>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return MSOC_OK;
 }
 
-int msoc_step(msoc_handle *h, const float *d_actions, const float *d_obs_in, float *d_obs_out, float *d_reward,
-              uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags, void *stream)
+/* the three launches of one step over the envs [e0, e1): `st` carries the fast and the heavy kernel, lane `k` of the
+   handle's auxiliary streams the light kernel */
+static int launch_step(msoc_handle *h, StepParams &P, int64_t e0, int64_t e1, int chunk, int k, cudaStream_t st)
 {
-    if (!h || !d_actions || !d_obs_in || !d_obs_out || !d_reward || !d_done || !d_goal)
-        return fail(MSOC_ERR_INVALID, "msoc_step: null argument");
-    DeviceGuard guard(h->device);
-    StepParams P;
-    P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_in = d_obs_in; P.obs_out = d_obs_out;
-    P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
-    P.global_offset = h->global_offset; P.flags = flags; P.cur = h->cur;
-    P.ctl = h->d_ctl + 4 * h->step_parity; P.ctl_other = h->d_ctl + 4 * (h->step_parity ^ 1); P.list = h->d_list;
-    h->step_parity ^= 1;
-    const int64_t n_tiles = (h->n + FAST_BLOCK - 1) / FAST_BLOCK;
-    msoc_step_fast_kernel<<<(unsigned)n_tiles, FAST_BLOCK, FAST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    P.e0 = e0; P.e1 = e1; P.chunk = chunk;
+    const int64_t m = e1 - e0;
+    msoc_step_fast_kernel<<<(unsigned)((m + FAST_BLOCK - 1) / FAST_BLOCK), FAST_BLOCK, FAST_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     /* The two contact kernels only depend on the fast kernel's list.  The heavy one (few, long, latency-bound
        batches: one per warp) goes first and stays on the caller's stream; the light one runs beside it on the
        handle's own stream and fills the SMs as the heavy blocks drain.  The caller's stream then waits for it. */
-    cudaStream_t st = (cudaStream_t)stream;
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
-    const int64_t heavy_blocks_max = (h->n + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
+    const int64_t heavy_blocks_max = (m + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
     const unsigned grid = (unsigned)(heavy_blocks_max < resident ? heavy_blocks_max : resident);
-    CUDA_TRY(cudaEventRecord(h->ev_listed, st));
+    CUDA_TRY(cudaEventRecord(h->ev_listed[k], st));
     msoc_step_contact_kernel<<<grid, HEAVY_BLOCK, STEP_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_listed, 0));
+    CUDA_TRY(cudaStreamWaitEvent(h->aux_stream[k], h->ev_listed[k], 0));
     const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
-    const int64_t light_blocks_max = (h->n + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
-    msoc_step_light_kernel<<<(unsigned)(light_blocks_max < light_resident ? light_blocks_max : light_resident), LIGHT_BLOCK, LIGHT_SMEM_BYTES, h->aux_stream>>>(P);
+    const int64_t light_blocks_max = (m + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
+    msoc_step_light_kernel<<<(unsigned)(light_blocks_max < light_resident ? light_blocks_max : light_resident), LIGHT_BLOCK, LIGHT_SMEM_BYTES, h->aux_stream[k]>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(h->ev_light, h->aux_stream));
-    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_light, 0));
-    h->cur ^= 1;
+    CUDA_TRY(cudaEventRecord(h->ev_light[k], h->aux_stream[k]));
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_light[k], 0));
+    return MSOC_OK;
+}
+
+static void fill_step_params(msoc_handle *h, StepParams &P, const float *d_actions, float *d_obs_out, float *d_frames_out,
+                             float *d_reward, uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags)
+{
+    P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_out = d_obs_out; P.frames_out = d_frames_out;
+    P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
+    P.global_offset = h->global_offset; P.flags = flags;
+    P.ctl = h->d_ctl; P.list = h->d_list;
+}
+
+int msoc_step(msoc_handle *h, const float *d_actions, float *d_obs_out, float *d_reward,
+              uint8_t *d_done, int8_t *d_goal, int32_t *d_score, uint32_t flags, void *stream)
+{
+    if (!h || !d_actions || !d_obs_out || !d_reward || !d_done || !d_goal)
+        return fail(MSOC_ERR_INVALID, "msoc_step: null argument");
+    DeviceGuard guard(h->device);
+    StepParams P;
+    fill_step_params(h, P, d_actions, d_obs_out, nullptr, d_reward, d_done, d_goal, d_score, flags);
+    return launch_step(h, P, 0, h->n, -1, 0, (cudaStream_t)stream);
+}
+
+/* Host-buffer step: the envs are cut into chunks that alternate between two stream lanes, so that the H2D copy and the
+   kernels of one chunk run while the D2H copies of the previous one are still on the wire. */
+static int step_host_impl(msoc_handle *h, const float *h_actions, float *h_obs, float *h_frames, float *h_reward, uint8_t *h_done,
+                          int8_t *h_goal, int32_t *h_score, uint32_t flags, void *stream)
+{
+    if (!h || !h_actions) return fail(MSOC_ERR_INVALID, "msoc_step_host: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h_frames && !h->d_frames) {
+        cudaError_t ce = cudaMalloc(&h->d_frames, (size_t)h->n * 4 * FRAME * sizeof(float));
+        if (ce != cudaSuccess) return fail(MSOC_ERR_ALLOC, "msoc_step_host_frames: cudaMalloc", ce);
+    }
+    StepParams P;
+    fill_step_params(h, P, h->d_act, h->d_obs, h_frames ? h->d_frames : nullptr, h->d_rew, h->d_done, h->d_goal, h->d_score, flags);
+    /* chunks of at least 64 Ki envs, at most MAX_CHUNKS */
+    int chunks = (int)(h->n / 65536);
+    if (chunks < 1) chunks = 1;
+    if (chunks > MAX_CHUNKS) chunks = MAX_CHUNKS;
+    const int64_t per = ((h->n + chunks - 1) / chunks + 127) & ~(int64_t)127;
+    auto copies_back = [&](int64_t e0, int64_t m, cudaStream_t s) -> int {
+        if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs + e0 * 4 * OBS, h->d_obs + e0 * 4 * OBS, (size_t)m * 4 * OBS * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_frames) CUDA_TRY(cudaMemcpyAsync(h_frames + e0 * 4 * FRAME, h->d_frames + e0 * 4 * FRAME, (size_t)m * 4 * FRAME * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward + e0 * 2, h->d_rew + e0 * 2, (size_t)m * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done + e0, h->d_done + e0, (size_t)m, cudaMemcpyDeviceToHost, s));
+        if (h_goal) CUDA_TRY(cudaMemcpyAsync(h_goal + e0, h->d_goal + e0, (size_t)m, cudaMemcpyDeviceToHost, s));
+        if (h_score) CUDA_TRY(cudaMemcpyAsync(h_score + e0 * 2, h->d_score + e0 * 2, (size_t)m * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        return MSOC_OK;
+    };
+    if (chunks == 1) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_act, h_actions, (size_t)h->n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+        int rc = launch_step(h, P, 0, h->n, -1, 0, st);
+        if (rc != MSOC_OK) return rc;
+        rc = copies_back(0, h->n, st);
+        if (rc != MSOC_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return MSOC_OK;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_ctl + CTL_CHUNK0, 0, CTL_WORDS * MAX_CHUNKS * sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev_pipe_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(h->pipe_stream, h->ev_pipe_fork, 0));
+    for (int c = 0; c < chunks; c++) {
+        const int64_t e0 = c * per, e1 = (e0 + per < h->n) ? e0 + per : h->n;
+        if (e0 >= e1) break;
+        cudaStream_t s = (c & 1) ? h->pipe_stream : st;
+        CUDA_TRY(cudaMemcpyAsync(h->d_act + e0 * 12, h_actions + e0 * 12, (size_t)(e1 - e0) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+        int rc = launch_step(h, P, e0, e1, c, c & 1, s);
+        if (rc != MSOC_OK) return rc;
+        rc = copies_back(e0, e1 - e0, s);
+        if (rc != MSOC_OK) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_pipe_join, h->pipe_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_pipe_join, 0));
+    msoc_advance_kernel<<<1, 1, 0, st>>>(h->d_ctl);
+    g_launches++;
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
     return MSOC_OK;
 }
 
 int msoc_step_host(msoc_handle *h, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done,
                    int8_t *h_goal, int32_t *h_score, uint32_t flags, void *stream)
 {
-    if (!h || !h_actions) return fail(MSOC_ERR_INVALID, "msoc_step_host: null argument");
-    DeviceGuard guard(h->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)h->n;
-    CUDA_TRY(cudaMemcpyAsync(h->d_act, h_actions, n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = msoc_step(h, h->d_act, h->d_obs, h->d_obs, h->d_rew, h->d_done, h->d_goal, h->d_score, flags, stream);
-    if (rc != MSOC_OK) return rc;
-    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, n * 4 * OBS * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, h->d_rew, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-    if (h_goal) CUDA_TRY(cudaMemcpyAsync(h_goal, h->d_goal, n, cudaMemcpyDeviceToHost, st));
-    if (h_score) CUDA_TRY(cudaMemcpyAsync(h_score, h->d_score, n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return MSOC_OK;
+    return step_host_impl(h, h_actions, h_obs, nullptr, h_reward, h_done, h_goal, h_score, flags, stream);
+}
+
+int msoc_step_host_frames(msoc_handle *h, const float *h_actions, float *h_frames, float *h_reward, uint8_t *h_done,
+                          int8_t *h_goal, int32_t *h_score, uint32_t flags, void *stream)
+{
+    if (!h_frames) return fail(MSOC_ERR_INVALID, "msoc_step_host_frames: null frame buffer");
+    return step_host_impl(h, h_actions, nullptr, h_frames, h_reward, h_done, h_goal, h_score, flags, stream);
 }
 
 int msoc_reset_host(msoc_handle *h, const uint8_t *h_mask, int mode, int has_seed, uint64_t seed, float *h_obs, void *stream)
@@ -734,12 +948,18 @@ int msoc_read_counters(msoc_handle *h, int32_t *h_score, int32_t *h_steps, void 
     if (!h) return fail(MSOC_ERR_INVALID, "msoc_read_counters: null handle");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<int4> tmp((size_t)h->n);
-    CUDA_TRY(cudaMemcpy2DAsync(tmp.data(), sizeof(int4), h->A.misc + 2, 4 * sizeof(float4), sizeof(int4), (size_t)h->n, cudaMemcpyDeviceToHost, st));
+    int step = 0;
+    CUDA_TRY(cudaMemcpyAsync(&step, h->d_ctl + CTL_STEP_FAST, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < h->n; i++) {
-        if (h_steps) h_steps[i] = tmp[(size_t)i].x;
-        if (h_score) { h_score[2 * i] = tmp[(size_t)i].y; h_score[2 * i + 1] = tmp[(size_t)i].z; }
+    if (h_steps) {
+        std::vector<float4> tmp((size_t)h->n);
+        CUDA_TRY(cudaMemcpy2DAsync(tmp.data(), sizeof(float4), h->A.pose[step % 3] + 7, POSE_F4 * sizeof(float4), sizeof(float4), (size_t)h->n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < h->n; i++) { int32_t v; memcpy(&v, &tmp[(size_t)i].y, 4); h_steps[i] = v; }
+    }
+    if (h_score) {
+        CUDA_TRY(cudaMemcpyAsync(h_score, h->A.score, (size_t)h->n * sizeof(int2), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
     }
     return MSOC_OK;
 }
@@ -776,11 +996,18 @@ int msoc_get_state(msoc_handle *h, const int64_t *h_idx, int64_t n, msoc_env_sta
     msoc_env_state *d_s = (msoc_env_state *)((char *)h->d_stage + ib);
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(d_idx, h_idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
-    msoc_get_state_kernel<<<(unsigned)((n + 127) / 128), 128>>>(h->A, h->cur, d_idx, n, d_s);
+    msoc_get_state_kernel<<<(unsigned)((n + 127) / 128), 128>>>(h->A, h->d_ctl, d_idx, n, d_s);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(h_out, d_s, sb, cudaMemcpyDeviceToHost));
     return MSOC_OK;
+}
+
+static float wrap_host(float x)
+{
+    double a = (double)x;
+    if (a > 3.14159274101257324 || a < -3.14159274101257324) a = atan2(sin(a), cos(a));
+    return (float)a;
 }
 
 int msoc_set_state(msoc_handle *h, const int64_t *h_idx, int64_t n, const msoc_env_state *h_in)
@@ -789,6 +1016,11 @@ int msoc_set_state(msoc_handle *h, const int64_t *h_idx, int64_t n, const msoc_e
     if (rc != MSOC_OK) return rc;
     if (!h_in) return fail(MSOC_ERR_INVALID, "msoc_set_state: null input");
     DeviceGuard guard(h->device);
+    if (!h->d_inject) { /* records of injected states whose pose differs from the newest emitted frame's */
+        cudaError_t ce = cudaMalloc(&h->d_inject, (size_t)h->n * POSE_F4 * sizeof(float4));
+        if (ce != cudaSuccess) return fail(MSOC_ERR_ALLOC, "msoc_set_state: cudaMalloc", ce);
+        h->A.inject = (float4 *)h->d_inject;
+    }
     const size_t ib = align_up((size_t)n * sizeof(int64_t)), sb = (size_t)n * sizeof(msoc_env_state);
     rc = ensure_stage(h, ib + sb);
     if (rc != MSOC_OK) return rc;
@@ -798,14 +1030,13 @@ int msoc_set_state(msoc_handle *h, const int64_t *h_idx, int64_t n, const msoc_e
     std::vector<msoc_env_state> tmp(h_in, h_in + n);
     for (auto &S : tmp)
         for (int i = 0; i < 4; i++) {
-            double a = (double)S.ang[i];
-            if (a > 3.14159274101257324 || a < -3.14159274101257324) a = atan2(sin(a), cos(a));
-            S.ang[i] = (float)a;
+            S.ang[i] = wrap_host(S.ang[i]);
+            for (int k = 0; k < 2; k++) S.hist_ang[k][i] = wrap_host(S.hist_ang[k][i]);
         }
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(d_idx, h_idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_s, tmp.data(), sb, cudaMemcpyHostToDevice));
-    msoc_set_state_kernel<<<(unsigned)((n + 127) / 128), 128>>>(h->A, h->cur, d_idx, n, d_s);
+    msoc_set_state_kernel<<<(unsigned)((n + 127) / 128), 128>>>(h->A, h->d_ctl, d_idx, n, d_s);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
@@ -816,21 +1047,19 @@ int msoc_get_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, float *h_
 {
     int rc = check_idx(h, h_idx, n, "msoc_get_obs_host: bad argument");
     if (rc != MSOC_OK) return rc;
+    if (!h_obs) return fail(MSOC_ERR_INVALID, "msoc_get_obs_host: null output");
     DeviceGuard guard(h->device);
-    CUDA_TRY(cudaDeviceSynchronize());
-    for (int64_t i = 0; i < n; i++)
-        CUDA_TRY(cudaMemcpy(h_obs + i * 4 * OBS, h->d_obs + h_idx[i] * 4 * OBS, 4 * OBS * sizeof(float), cudaMemcpyDeviceToHost));
-    return MSOC_OK;
-}
-
-int msoc_set_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, const float *h_obs)
-{
-    int rc = check_idx(h, h_idx, n, "msoc_set_obs_host: bad argument");
+    const size_t ib = align_up((size_t)n * sizeof(int64_t)), ob = (size_t)n * 4 * OBS * sizeof(float);
+    rc = ensure_stage(h, ib + ob);
     if (rc != MSOC_OK) return rc;
-    DeviceGuard guard(h->device);
+    int64_t *d_idx = (int64_t *)h->d_stage;
+    float *d_o = (float *)((char *)h->d_stage + ib);
     CUDA_TRY(cudaDeviceSynchronize());
-    for (int64_t i = 0; i < n; i++)
-        CUDA_TRY(cudaMemcpy(h->d_obs + h_idx[i] * 4 * OBS, h_obs + i * 4 * OBS, 4 * OBS * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_idx, h_idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    msoc_gather_obs_kernel<<<(unsigned)((n * 4 * OBS + 255) / 256), 256>>>(h->d_obs, d_idx, n, d_o);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(h_obs, d_o, ob, cudaMemcpyDeviceToHost));
     return MSOC_OK;
 }
 

@@ -74,6 +74,10 @@ constexpr float E_BALL_WALL = (float)(0.95 * 0.95), U_BALL_WALL = (float)(0.2 * 
 
 /* flags word of the per-env counters */
 constexpr uint32_t FLAG_CACHE_MASK = 63u, FLAG_MODE_SHIFT = 6, FLAG_MODE_MASK = 3u << 6, FLAG_HAS_BIAS = 1u << 8;
+/* set in the CURRENT record of an env whose state was injected after its newest frame had been emitted
+   (msoc_set_state): the record keeps the pose behind that frame, the state the next step starts from is in
+   Arrays::inject */
+constexpr uint32_t FLAG_INJECT = 1u << 9;
 
 /* device-side config: config.json keys as floats plus derived reciprocals */
 struct SimCfg {
@@ -82,22 +86,42 @@ struct SimCfg {
     float prox_mult, move_mult, goal_reward, conceded_penalty, alive_penalty, score_diff_mult;
     int32_t max_steps;
     int32_t pad;
+    float inv_vmax, inv_wmax; /* 1 / max(max_velocity, 1e-6), 1 / max(max_angular_velocity, 1e-6) (game/game.py:262-264) */
 };
+MSOC_HD void cfg_derive(SimCfg &s)
+{
+    s.inv_vmax = 1.0f / fmaxf(s.max_velocity, 1e-6f);
+    s.inv_wmax = 1.0f / fmaxf(s.max_ang_vel, 1e-6f);
+}
 
-/* struct-of-arrays state of N envs (device memory in the product, host memory in tests/hostsim) */
+/* State of N envs (device memory in the product, host memory in tests/hostsim).
+
+   An env's state is one 128-byte record; the records live in THREE buffers that rotate: step t reads the state from
+   buffer t % 3 and writes the new one to buffer (t + 1) % 3, so after the store the three buffers hold the states of
+   steps t-2, t-1 and t -- exactly the poses behind the three frames of the stacked observation
+   (soccer_env.py:130-140).  The observation is therefore REBUILT from the three records (3 x 128 B read, L2 hits for
+   two of them) instead of being shifted through memory (704 B of 8-byte-aligned history reads per env-step), and a
+   frame is the same arithmetic on the same fp32 inputs whenever it is rebuilt: bit-identical to the frame emitted one
+   and two steps earlier.  A fresh episode writes its first state to all three buffers (soccer_env.py:92-96). */
+constexpr int POSE_F4 = 8; /* float4s per env record: 128 B = one L2 line = four DRAM sectors */
 struct Arrays {
     int64_t n;
-    /* Records of an env are contiguous: the contact kernels touch scattered envs, and a record that fills whole 32-byte
-       sectors costs them half the DRAM traffic of one 16-byte field per array (the fast kernel, which walks consecutive
-       envs, reads the same bytes either way). */
-    float4 *bodies;    /* 5 per env: (px, py, vx, vy) of agent_0..3, ball */
-    float4 *misc;      /* 4 per env: agent angles (wrapped); agent angular velocities; (steps, score_blue, score_red, flags)
-                          as bits; (ball angular velocity, running episode return, -, -) */
-    float4 *bias;      /* 4 per env, contiguous: v_bias agents 0-1, 2-3; (v_bias ball, w_bias agents 0-1); (w_bias agents 2-3, -, -) */
+    float4 *pose[3];   /* per env 8 float4: (px, py, vx, vy) of agent_0..3, ball; agent angles (wrapped); agent angular
+                          velocities; (ball angular velocity, steps, flags, running episode return) as bits.
+                          flags: arbiter-cache count, spawn mode, has-bias, inject */
+    int2 *score;       /* (blue, red), in place: read every step, written on goals and resets only */
+    float4 *bias;      /* 4 per env, in place: v_bias agents 0-1, 2-3; (v_bias ball, w_bias agents 0-1); (w_bias agents 2-3, -, -);
+                          touched only while the has-bias flag is set */
+    float4 *inject;    /* 8 per env or null: the record the next step starts from, for envs flagged FLAG_INJECT */
     uint64_t *seed;    /* per-env Philox key */
     uint32_t *spawn_count;
-    uint32_t *cache[2]; /* arbiter cache, ping-pong between steps: entry j of env e = 3 words at cache_slot(e, j) */
+    uint32_t *cache[2]; /* arbiter cache, ping-pong by step parity: entry j of env e = 3 words at cache_slot(e, j) */
 };
+/* the step counter lives in device memory and cycles through 0..5 (period of the buffer rotation and of the parity) */
+MSOC_HD int buf_prev(int step) { return (step + 2) % 3; } /* state of two steps ago -> oldest frame */
+MSOC_HD int buf_cur(int step) { return step % 3; }        /* state the step starts from -> middle frame */
+MSOC_HD int buf_next(int step) { return (step + 1) % 3; } /* receives the new state -> newest frame */
+MSOC_HD int cache_half(int step) { return step & 1; }
 
 struct Env {
     float px[5], py[5], vx[5], vy[5];
@@ -153,8 +177,16 @@ MSOC_HD float rsqrt_f(float x)
 }
 MSOC_HD float wrap_angle(float a)
 {
+    /* one turn: the common case (|w dt| < pi), bit-for-bit the two-term Cody-Waite subtraction */
     if (a > PI_F) a = (a - TWO_PI_HI) - TWO_PI_LO;
     else if (a < -PI_F) a = (a + TWO_PI_HI) + TWO_PI_LO;
+    /* several turns in one step (configs with a huge action_torque_max: the reference default of 100000 spins an
+       agent by ~27 rad per step): full range reduction a - 2 pi rint(a / 2 pi), hi/lo split */
+    if (fabsf(a) > PI_F) {
+        const float k = rintf(a * 0.15915494309189535f);
+        a = fmaf(-k, TWO_PI_HI, a);
+        a = fmaf(-k, TWO_PI_LO, a);
+    }
     return a;
 }
 
@@ -235,20 +267,47 @@ MSOC_HD float u2f(uint32_t u)
 }
 
 /* -------------------------------------------------------------------------------- state load/store */
-MSOC_HD void load_env(const Arrays &A, int64_t e, Env &E)
+/* what an observation frame is made of (game/game.py:266-321): positions of the five bodies, velocity, angle and
+   angular velocity of the four agents */
+struct Pose { float px[5], py[5], vx[4], vy[4], ang[4], w[4]; };
+
+MSOC_HD void pose_of(const Env &E, Pose &P)
+{
+#pragma unroll
+    for (int i = 0; i < 5; i++) { P.px[i] = E.px[i]; P.py[i] = E.py[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { P.vx[i] = E.vx[i]; P.vy[i] = E.vy[i]; P.ang[i] = E.ang[i]; P.w[i] = E.w[i]; }
+}
+/* the first seven float4 of an env record */
+MSOC_HD void pose_unpack(const float4 *r, Pose &P)
+{
+#pragma unroll
+    for (int i = 0; i < 5; i++) { P.px[i] = r[i].x; P.py[i] = r[i].y; if (i < 4) { P.vx[i] = r[i].z; P.vy[i] = r[i].w; } }
+    P.ang[0] = r[5].x; P.ang[1] = r[5].y; P.ang[2] = r[5].z; P.ang[3] = r[5].w;
+    P.w[0] = r[6].x; P.w[1] = r[6].y; P.w[2] = r[6].z; P.w[3] = r[6].w;
+}
+MSOC_HD void pose_pack(const Pose &P, float ball_vx, float ball_vy, float4 *r)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = make_float4(P.px[i], P.py[i], P.vx[i], P.vy[i]);
+    r[4] = make_float4(P.px[4], P.py[4], ball_vx, ball_vy);
+    r[5] = make_float4(P.ang[0], P.ang[1], P.ang[2], P.ang[3]);
+    r[6] = make_float4(P.w[0], P.w[1], P.w[2], P.w[3]);
+}
+
+MSOC_HD void load_env(const Arrays &A, const float4 *rec, int64_t e, Env &E)
 {
 #pragma unroll
     for (int i = 0; i < 5; i++) {
-        const float4 b = A.bodies[e * 5 + i];
+        const float4 b = rec[i];
         E.px[i] = b.x; E.py[i] = b.y; E.vx[i] = b.z; E.vy[i] = b.w;
     }
-    const float4 a = A.misc[e * 4], w = A.misc[e * 4 + 1], cbits = A.misc[e * 4 + 2], brw = A.misc[e * 4 + 3];
-    const float2 br = make_float2(brw.x, brw.y);
-    const int4 c = make_int4((int)f2u(cbits.x), (int)f2u(cbits.y), (int)f2u(cbits.z), (int)f2u(cbits.w));
+    const float4 a = rec[5], w = rec[6], c = rec[7];
+    const int2 sc = A.score[e];
     E.ang[0] = a.x; E.ang[1] = a.y; E.ang[2] = a.z; E.ang[3] = a.w;
     E.w[0] = w.x; E.w[1] = w.y; E.w[2] = w.z; E.w[3] = w.w;
-    E.w[4] = br.x; E.ep_return = br.y;
-    E.steps = c.x; E.score_b = c.y; E.score_r = c.z; E.flags = (uint32_t)c.w;
+    E.w[4] = c.x; E.steps = (int32_t)f2u(c.y); E.flags = f2u(c.z); E.ep_return = c.w;
+    E.score_b = sc.x; E.score_r = sc.y;
     if (E.flags & FLAG_HAS_BIAS) {
         const float4 *bp = A.bias + 4 * e;
         const float4 b01 = bp[0], b23 = bp[1], b4w = bp[2], w23 = bp[3];
@@ -264,7 +323,8 @@ MSOC_HD void load_env(const Arrays &A, int64_t e, Env &E)
     }
 }
 
-MSOC_HD void store_env(const Arrays &A, int64_t e, Env &E)
+/* in-place part of the store: the bias velocities (only when there are any) and the has-bias flag */
+MSOC_HD void store_env_bias(const Arrays &A, int64_t e, Env &E)
 {
     bool any_bias = false;
 #pragma unroll
@@ -281,131 +341,66 @@ MSOC_HD void store_env(const Arrays &A, int64_t e, Env &E)
     } else {
         E.flags &= ~FLAG_HAS_BIAS;
     }
+}
+/* the env record (after store_env_bias) */
+MSOC_HD void store_env_record(float4 *rec, const Env &E)
+{
 #pragma unroll
-    for (int i = 0; i < 5; i++) A.bodies[e * 5 + i] = make_float4(E.px[i], E.py[i], E.vx[i], E.vy[i]);
-    A.misc[e * 4] = make_float4(E.ang[0], E.ang[1], E.ang[2], E.ang[3]);
-    A.misc[e * 4 + 1] = make_float4(E.w[0], E.w[1], E.w[2], E.w[3]);
-    A.misc[e * 4 + 2] = make_float4(u2f((uint32_t)E.steps), u2f((uint32_t)E.score_b), u2f((uint32_t)E.score_r), u2f(E.flags));
-    A.misc[e * 4 + 3] = make_float4(E.w[4], E.ep_return, 0.0f, 0.0f);
+    for (int i = 0; i < 5; i++) rec[i] = make_float4(E.px[i], E.py[i], E.vx[i], E.vy[i]);
+    rec[5] = make_float4(E.ang[0], E.ang[1], E.ang[2], E.ang[3]);
+    rec[6] = make_float4(E.w[0], E.w[1], E.w[2], E.w[3]);
+    rec[7] = make_float4(E.w[4], u2f((uint32_t)E.steps), u2f(E.flags), E.ep_return);
+}
+/* bias, record into buffer `buf`, and the score when the caller says it changed (goal, reset, injection) */
+MSOC_HD void store_env(const Arrays &A, int buf, int64_t e, Env &E, bool score_dirty)
+{
+    store_env_bias(A, e, E);
+    store_env_record(A.pose[buf] + e * POSE_F4, E);
+    if (score_dirty) A.score[e] = make_int2(E.score_b, E.score_r);
 }
 
 /* ----------------------------------------------------------------------------- observation frame */
 /* game/game.py:258-322; frames for all four agents, 22 floats each.  Pairwise agent vectors are
-   computed once and mirrored.  STRIDE is the distance between two agents' frames in `out`. */
+   computed once and mirrored.  STRIDE is the distance between two agents' frames in `out`.
+   The sum of squares is an explicit fma: a frame is rebuilt from its pose by whichever kernel finishes the env one and
+   two steps later (Arrays), and must come out bit-identical there whatever the compiler contracts. */
 MSOC_HD void unit_mag(float dx, float dy, float &ux, float &uy, float &mag)
 {
-    const float d2 = dx * dx + dy * dy;
+    const float d2 = fmaf(dx, dx, dy * dy);
     if (d2 > 1e-16f) { /* mag > 1e-8, game/game.py:281 */
         const float inv = rsqrt_f(d2);
         ux = dx * inv; uy = dy * inv; mag = d2 * inv * 0.001f; /* / hypot(800, 600) */
     } else { ux = 0.0f; uy = 0.0f; mag = 0.0f; }
 }
 
-template <int STRIDE>
-MSOC_HD void make_frames(const Env &E, const SimCfg &c, float *out)
+MSOC_HD float4 ld_f4(const float4 *p, bool cg)
 {
-    const float vmax = fmaxf(c.max_velocity, 1e-6f), wmax = fmaxf(c.max_ang_vel, 1e-6f);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float *o = out + i * STRIDE;
-        o[0] = E.vx[i] / vmax;
-        o[1] = E.vy[i] / vmax;
-        o[2] = E.ang[i] / PI_F;
-        o[3] = E.w[i] / wmax;
-    }
-    /* agent-agent vectors: slot of j in i's frame */
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int j = i + 1; j < 4; j++) {
-            float ux, uy, m;
-            unit_mag(E.px[j] - E.px[i], E.py[j] - E.py[i], ux, uy, m);
-            /* teammate: 0<->1, 2<->3 (slot 4); opponents in index order (slots 7, 10) */
-            const bool mates = (i == 0 && j == 1) || (i == 2 && j == 3);
-            const int slot_i = mates ? 4 : (7 + 3 * (j & 1)); /* i sees opponent j: j=2/0 -> 7, j=3/1 -> 10 */
-            const int slot_j = mates ? 4 : (7 + 3 * (i & 1));
-            float *oi = out + i * STRIDE + slot_i, *oj = out + j * STRIDE + slot_j;
-            oi[0] = ux; oi[1] = uy; oi[2] = m;
-            oj[0] = -ux; oj[1] = -uy; oj[2] = m;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float *o = out + i * STRIDE;
-        unit_mag(E.px[4] - E.px[i], E.py[4] - E.py[i], o[13], o[14], o[15]);
-        const float own_x = (i < 2) ? FIELD_L : FIELD_R, opp_x = (i < 2) ? FIELD_R : FIELD_L;
-        unit_mag(own_x - E.px[i], 300.0f - E.py[i], o[16], o[17], o[18]);
-        unit_mag(opp_x - E.px[i], 300.0f - E.py[i], o[19], o[20], o[21]);
-    }
+#if defined(__CUDA_ARCH__)
+    return cg ? __ldcg(p) : *p; /* cg: from L2 (records another lane of the warp has just written) */
+#else
+    (void)cg; return *p;
+#endif
 }
-
-/* One agent's frame (22 floats); same values as make_frames, used by the kernels to stage the
-   observation write agent by agent (pair vectors are recomputed instead of kept in registers). */
-template <int I>
-MSOC_HD void make_frame_agent(const Env &E, const SimCfg &c, float *o)
+/* Frame of agent a (22 floats) from an env record.  Scaled by reciprocals (within 1.5 ulp of the reference's
+   divisions).  u(p_j - p_i) = -u(p_i - p_j) exactly, so the four agents' frames are consistent with each other. */
+MSOC_HD void frame_of_record(const float4 *rec, int a, bool cg, const SimCfg &c, float *o)
 {
-    const float vmax = fmaxf(c.max_velocity, 1e-6f), wmax = fmaxf(c.max_ang_vel, 1e-6f);
-    o[0] = E.vx[I] / vmax;
-    o[1] = E.vy[I] / vmax;
-    o[2] = E.ang[I] / PI_F;
-    o[3] = E.w[I] / wmax;
-    constexpr int MATE = (I == 0) ? 1 : (I == 1) ? 0 : (I == 2) ? 3 : 2;
-    constexpr int OPP0 = (I < 2) ? 2 : 0, OPP1 = (I < 2) ? 3 : 1;
-    /* mirror make_frames exactly: pair (lo, hi) is computed as hi - lo and negated for hi's frame */
-    {
-        float ux, uy, m;
-        constexpr int LO = I < MATE ? I : MATE, HI = I < MATE ? MATE : I;
-        unit_mag(E.px[HI] - E.px[LO], E.py[HI] - E.py[LO], ux, uy, m);
-        o[4] = (I == LO) ? ux : -ux; o[5] = (I == LO) ? uy : -uy; o[6] = m;
-    }
-    {
-        float ux, uy, m;
-        constexpr int LO = I < OPP0 ? I : OPP0, HI = I < OPP0 ? OPP0 : I;
-        unit_mag(E.px[HI] - E.px[LO], E.py[HI] - E.py[LO], ux, uy, m);
-        o[7] = (I == LO) ? ux : -ux; o[8] = (I == LO) ? uy : -uy; o[9] = m;
-    }
-    {
-        float ux, uy, m;
-        constexpr int LO = I < OPP1 ? I : OPP1, HI = I < OPP1 ? OPP1 : I;
-        unit_mag(E.px[HI] - E.px[LO], E.py[HI] - E.py[LO], ux, uy, m);
-        o[10] = (I == LO) ? ux : -ux; o[11] = (I == LO) ? uy : -uy; o[12] = m;
-    }
-    unit_mag(E.px[4] - E.px[I], E.py[4] - E.py[I], o[13], o[14], o[15]);
-    constexpr float own_x = (I < 2) ? FIELD_L : FIELD_R, opp_x = (I < 2) ? FIELD_R : FIELD_L;
-    unit_mag(own_x - E.px[I], 300.0f - E.py[I], o[16], o[17], o[18]);
-    unit_mag(opp_x - E.px[I], 300.0f - E.py[I], o[19], o[20], o[21]);
-}
-
-/* Frame of agent `a` (runtime index) from an env snapshot stored field-major with stride `st`:
-   snap[(f)*st], f = 0-4 px, 5-9 py, 10-13 vx, 14-17 vy, 18-21 angle, 22-25 angular velocity.
-   Same arithmetic as make_frames (u(p_j - p_i) = -u(p_i - p_j) exactly). */
-constexpr int SNAP_FIELDS = 26;
-MSOC_HD void snapshot_env(const Env &E, float *snap, int st)
-{
-#pragma unroll
-    for (int i = 0; i < 5; i++) { snap[i * st] = E.px[i]; snap[(5 + i) * st] = E.py[i]; }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        snap[(10 + i) * st] = E.vx[i]; snap[(14 + i) * st] = E.vy[i];
-        snap[(18 + i) * st] = E.ang[i]; snap[(22 + i) * st] = E.w[i];
-    }
-}
-MSOC_HD void make_frame_dyn(const float *snap, int st, int a, const SimCfg &c, float *o)
-{
-    const float vmax = fmaxf(c.max_velocity, 1e-6f), wmax = fmaxf(c.max_ang_vel, 1e-6f);
-    const float x = snap[a * st], y = snap[(5 + a) * st];
-    o[0] = snap[(10 + a) * st] / vmax;
-    o[1] = snap[(14 + a) * st] / vmax;
-    o[2] = snap[(18 + a) * st] / PI_F;
-    o[3] = snap[(22 + a) * st] / wmax;
-    const int opp0 = (a < 2) ? 2 : 0;
-    const int tgt[4] = {a ^ 1, opp0, opp0 + 1, 4};
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        unit_mag(snap[tgt[k] * st] - x, snap[(5 + tgt[k]) * st] - y, o[4 + 3 * k], o[5 + 3 * k], o[6 + 3 * k]);
+    const int opp = (a & 2) ^ 2;
+    const float4 own = ld_f4(rec + a, cg), mate = ld_f4(rec + (a ^ 1), cg), o0 = ld_f4(rec + opp, cg), o1 = ld_f4(rec + opp + 1, cg);
+    const float4 ball = ld_f4(rec + 4, cg), ang4 = ld_f4(rec + 5, cg), w4 = ld_f4(rec + 6, cg);
+    const float ang = a == 0 ? ang4.x : a == 1 ? ang4.y : a == 2 ? ang4.z : ang4.w;
+    const float w = a == 0 ? w4.x : a == 1 ? w4.y : a == 2 ? w4.z : w4.w;
+    o[0] = own.z * c.inv_vmax;
+    o[1] = own.w * c.inv_vmax;
+    o[2] = ang * 0.318309886183790672f;
+    o[3] = w * c.inv_wmax;
+    unit_mag(mate.x - own.x, mate.y - own.y, o[4], o[5], o[6]);
+    unit_mag(o0.x - own.x, o0.y - own.y, o[7], o[8], o[9]);
+    unit_mag(o1.x - own.x, o1.y - own.y, o[10], o[11], o[12]);
+    unit_mag(ball.x - own.x, ball.y - own.y, o[13], o[14], o[15]);
     const float own_x = (a < 2) ? FIELD_L : FIELD_R, opp_x = (a < 2) ? FIELD_R : FIELD_L;
-    unit_mag(own_x - x, 300.0f - y, o[16], o[17], o[18]);
-    unit_mag(opp_x - x, 300.0f - y, o[19], o[20], o[21]);
+    unit_mag(own_x - own.x, 300.0f - own.y, o[16], o[17], o[18]);
+    unit_mag(opp_x - own.x, 300.0f - own.y, o[19], o[20], o[21]);
 }
 
 /* ------------------------------------------------------------------------------------ narrow phase */
@@ -935,6 +930,7 @@ struct StepOut {
     uint8_t done;
     int8_t goal;
     bool fresh_episode;   /* auto-reset happened: obs = 3 copies of the new frame */
+    bool score_dirty;     /* the score changed (goal, auto-reset): store_env must write it */
     float finished_return; /* blue return of the episode that ended on this step */
     int n_contacts, overflow;
     int32_t score_b, score_r; /* info["score"] of this step (before any auto-reset) */
@@ -1092,9 +1088,11 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         if (contact_path) {
             /* work class for the contact queues: 0 = exactly one candidate pair and it is agent x segment
                (the bulk: an agent touching a wall), 1 = anything else (several pairs, agent x agent, ball) */
-            load = (popc32(m_as) == 1 && (m_aa | m_ba | m_bw) == 0u) ? 0 : 1;
+            load = (popc32(m_as) == 1 && (m_aa | m_ba | m_bw) == 0u && !(E.flags & FLAG_INJECT)) ? 0 : 1;
             return false;
         }
+        /* an injected state (Arrays::inject): the general kernel steps it (rare: only the step after msoc_set_state) */
+        if (E.flags & FLAG_INJECT) { load = 1; return false; }
     }
     if (!contact_path && old_count != 0) {
         /* nothing can touch this step, but the env still carries arbiters of contacts that ended
@@ -1413,7 +1411,7 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #pragma unroll
         for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
-    E.flags = (E.flags & ~FLAG_CACHE_MASK) | (uint32_t)new_count;
+    E.flags = (E.flags & ~(FLAG_CACHE_MASK | FLAG_INJECT)) | (uint32_t)new_count;
 
     /* ---- goal test (game/game.py:401-412), strict inequalities */
     int goal = 0;
@@ -1447,7 +1445,7 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
     }
     E.ep_return += r;
     out.reward = r; out.done = done ? 1 : 0; out.goal = (int8_t)goal;
-    out.fresh_episode = false; out.finished_return = 0.0f;
+    out.fresh_episode = false; out.finished_return = 0.0f; out.score_dirty = goal != 0;
     out.n_contacts = n_contacts; out.overflow = overflow;
     out.score_b = E.score_b; out.score_r = E.score_r;
     if (done) {
@@ -1457,7 +1455,7 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
             uint32_t sc = A.spawn_count[e];
             env_full_reset(E, 2, A.seed[e], gidx, sc);
             A.spawn_count[e] = sc;
-            out.fresh_episode = true;
+            out.fresh_episode = true; out.score_dirty = true;
         }
     }
     return true;

@@ -58,19 +58,18 @@ class HostBufferSim:
         _capi.check(self._L.msoc_get_state(self._h, idx.ctypes.data, len(idx), C.byref(arr)))
         return list(arr)
 
-    def set_states(self, idx, states, obs=None) -> None:
+    def set_states(self, idx, states) -> None:
+        """Injects states.  The observation history travels inside the state (hist_* poses, include/msoc.h):
+        with hist_valid = 0 the frames already emitted stay what they were."""
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         arr = (_capi.MsocEnvState * len(idx))(*states)
         _capi.check(self._L.msoc_set_state(self._h, idx.ctypes.data, len(idx), C.byref(arr)))
-        if obs is not None:
-            o = np.ascontiguousarray(obs, dtype=np.float32).reshape(len(idx), 4, 66)
-            _capi.check(self._L.msoc_set_obs_host(self._h, idx.ctypes.data, len(idx), o.ctypes.data))
 
     def get_state(self, i: int):
         return self.get_states([i])[0]
 
-    def set_state(self, i: int, S, obs=None) -> None:
-        self.set_states([i], [S], None if obs is None else np.asarray(obs, np.float32)[None])
+    def set_state(self, i: int, S) -> None:
+        self.set_states([i], [S])
 
     def get_obs(self, i: int) -> np.ndarray:
         idx = np.array([i], np.int64)

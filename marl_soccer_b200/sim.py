@@ -109,7 +109,7 @@ class BatchedSoccerSim:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if actions.numel() != self.num_envs * 12:
             raise ValueError(f"actions must have shape ({self.num_envs}, 4, 3), got {tuple(actions.shape)}")
-        _capi.check(self._L.msoc_step(self._h, actions.data_ptr(), self.obs.data_ptr(), self.obs.data_ptr(),
+        _capi.check(self._L.msoc_step(self._h, actions.data_ptr(), self.obs.data_ptr(),
                                       self.reward.data_ptr(), self.done.data_ptr(), self.goal.data_ptr(),
                                       self.score.data_ptr(), _capi.STEP_AUTO_RESET if auto_reset else 0,
                                       self._stream()))

@@ -722,6 +722,13 @@ void oracle_get_obs(const OracleEnv *E, float *obs)
             memcpy(obs + i * ORACLE_OBS + k * ORACLE_FRAME, E->frames[i][k], sizeof(float) * ORACLE_FRAME);
 }
 
+/* the four 22-float frames of the CURRENT bodies (game/game.py:258-322), without touching the 3-frame history:
+   lets the tests build the stacked observation that belongs to a given pair of history poses */
+void oracle_frames(const OracleEnv *E, float *frames)
+{
+    for (int i = 0; i < 4; i++) frame_for_agent(E, i, frames + i * ORACLE_FRAME);
+}
+
 void oracle_step(OracleEnv *E, const float *actions, float *obs, double *reward, uint8_t *done, int8_t *goal)
 {
     const OracleConfig *c = &E->cfg;

@@ -52,6 +52,7 @@ OracleEnv *oracle_create(const OracleConfig *cfg, uint64_t seed, uint64_t global
 void oracle_destroy(OracleEnv *E);
 void oracle_reset(OracleEnv *E, int mode, int has_seed, uint64_t seed);
 void oracle_get_obs(const OracleEnv *E, float *obs /* 4*66 */);
+void oracle_frames(const OracleEnv *E, float *frames /* 4*22, of the current bodies */);
 void oracle_step(OracleEnv *E, const float *actions /* 4*3 */, float *obs /* 4*66 or NULL */,
                  double *reward /* 2 */, uint8_t *done, int8_t *goal /* +1 blue, -1 red */);
 void oracle_get_state(const OracleEnv *E, OracleState *S);

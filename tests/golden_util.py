@@ -7,6 +7,7 @@ import numpy as np
 MAXC = 32
 FIELDS_F = ("pos", "vel", "ang", "angvel", "vbias", "wbias")
 FIELDS_I = ("steps", "mode", "spawn_count", "seed")
+HIST_F = ("pos", "vel", "ang", "angvel")
 
 
 def pack(states: list, prefix: str) -> dict:
@@ -27,6 +28,10 @@ def pack(states: list, prefix: str) -> dict:
             ci[i, j] = (p, key, age)
             cf[i, j] = (jn, jt)
     out[f"{prefix}_cache_n"], out[f"{prefix}_cache_i"], out[f"{prefix}_cache_f"] = cn, ci, cf
+    if all("hist" in s for s in states):  # the two poses behind the emitted frames t-2, t-1
+        for k in HIST_F:
+            out[f"{prefix}_hist_{k}"] = np.stack([np.stack([np.asarray(s["hist"][j][k], np.float64) for j in range(2)])
+                                                  for s in states])
     return out
 
 
@@ -41,5 +46,7 @@ def unpack(z, prefix: str) -> list:
         s["obs"] = np.array(z[f"{prefix}_obs"][i], np.float32)
         s["cache"] = [(int(a), int(b), int(c), float(z[f"{prefix}_cache_f"][i, j, 0]), float(z[f"{prefix}_cache_f"][i, j, 1]))
                       for j, (a, b, c) in enumerate(z[f"{prefix}_cache_i"][i][: int(z[f"{prefix}_cache_n"][i])])]
+        if f"{prefix}_hist_pos" in z:
+            s["hist"] = [{k: np.array(z[f"{prefix}_hist_{k}"][i][j]) for k in HIST_F} for j in range(2)]
         states.append(s)
     return states

@@ -39,7 +39,7 @@ def lib():
         L.hsim_create.argtypes = [C.POINTER(_capi.MsocConfig), i64, u64, u64, vp]
         L.hsim_destroy.argtypes = [vp]
         L.hsim_reset.argtypes = [vp, vp, C.c_int, C.c_int, u64, vp]
-        L.hsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
+        L.hsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
         L.hsim_stats.argtypes = [vp, vp, C.c_int]
         L.hsim_get_state.argtypes = [vp, i64, C.POINTER(_capi.MsocEnvState)]
         L.hsim_set_state.argtypes = [vp, i64, C.POINTER(_capi.MsocEnvState)]
@@ -77,7 +77,7 @@ class HostSim:
         done = np.zeros(self.n, np.uint8)
         goal = np.zeros(self.n, np.int8)
         self.score = np.zeros((self.n, 2), np.int32)
-        self._L.hsim_step(self._h, a.ctypes.data, self.obs.ctypes.data, out.ctypes.data, rew.ctypes.data,
+        self._L.hsim_step(self._h, a.ctypes.data, out.ctypes.data, rew.ctypes.data,
                           done.ctypes.data, goal.ctypes.data, self.score.ctypes.data, 1 if auto_reset else 0)
         self.obs = out
         return out.copy(), rew, done, goal
@@ -87,10 +87,8 @@ class HostSim:
         self._L.hsim_get_state(self._h, i, C.byref(S))
         return S
 
-    def set_state(self, i: int, S: _capi.MsocEnvState, obs=None) -> None:
+    def set_state(self, i: int, S: _capi.MsocEnvState) -> None:
         self._L.hsim_set_state(self._h, i, C.byref(S))
-        if obs is not None:
-            self.obs[i] = np.asarray(obs, np.float32).reshape(4, 66)
 
     def get_obs(self, i: int) -> np.ndarray:
         return self.obs[i].copy()

@@ -106,6 +106,7 @@ def lib():
     L.oracle_destroy.argtypes = [vp]
     L.oracle_reset.argtypes = [vp, C.c_int, C.c_int, u64]
     L.oracle_get_obs.argtypes = [vp, fp]
+    L.oracle_frames.argtypes = [vp, fp]
     L.oracle_step.argtypes = [vp, fp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int8)]
     L.oracle_get_state.argtypes = [vp, C.POINTER(OracleState)]
     L.oracle_set_state.argtypes = [vp, C.POINTER(OracleState)]
@@ -207,6 +208,12 @@ class OracleEnv:
     def obs(self) -> np.ndarray:
         o = np.zeros((4, OBS), np.float32)
         self._L.oracle_get_obs(self._h, o)
+        return o
+
+    def frames(self) -> np.ndarray:
+        """(4, 22): the frames of the current bodies; the 3-frame history is not touched."""
+        o = np.zeros((4, FRAME), np.float32)
+        self._L.oracle_frames(self._h, o)
         return o
 
     def step(self, actions):

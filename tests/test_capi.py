@@ -36,7 +36,7 @@ def test_header_symbols_exported(libpath):
 def test_version_and_error_string(libpath):
     L = C.CDLL(libpath)
     _capi.declare(L)
-    assert L.msoc_version() == 1
+    assert L.msoc_version() == 2
     assert isinstance(L.msoc_last_error(), bytes)
     assert L.msoc_launch_count() == 0
 

@@ -270,7 +270,7 @@ def test_vec_env_matches_single_envs_on_shared_actions():
     singles = [make_env(seed=3) for _ in range(n)]
     for i, e in enumerate(singles):
         e.reset()
-        e._sim.set_state(0, vec._sim.get_state(i), vec._sim.get_obs(i))
+        e._sim.set_state(0, vec._sim.get_state(i))  # the history poses travel in the state
     rng = np.random.default_rng(1)
     for t in range(30):
         a = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)

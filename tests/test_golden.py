@@ -1,4 +1,4 @@
-"""The committed golden vectors (tests/golden/step_v1.npz, made by tests/golden/make_golden.py from the CPU oracle:
+"""The committed golden vectors (tests/golden/step_v2.npz, made by tests/golden/make_golden.py from the CPU oracle:
 the reference itself cannot run here) against the oracle, the host build of the kernel
 arithmetic (CPU) and the CUDA kernels through the C-ABI (-m gpu)."""
 import os
@@ -10,7 +10,7 @@ import golden_util as G
 import oracle_lib as O
 import parity_util as P
 
-PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_v1.npz")
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_v2.npz")
 
 
 @pytest.fixture(scope="module")
@@ -58,7 +58,7 @@ def _check(sim_cls, gold):
             (gold["s0"], z["act1"], z["obs1"], z["rew1"], z["done1"], z["goal1"], gold["s1"]),
             (gold["s1"], z["act2"], z["obs2"], z["rew2"], z["done2"], z["goal2"], gold["s2"])):
         sim = sim_cls(n, P.CONFIG, seed=0)
-        sim.set_states(np.arange(n), [P.oracle_to_dev_state(s) for s in first], np.stack([s["obs"] for s in first]))
+        sim.set_states(np.arange(n), [P.oracle_to_dev_state(s) for s in first])
         o_d, r_d, d_d, g_d = sim.step(act, auto_reset=False)
         assert np.array_equal(d_d, done), "done flags differ from the golden vectors"
         assert np.array_equal(g_d, goal), "goal flags differ from the golden vectors"
