@@ -201,26 +201,34 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
         sectors; nothing is ever read back or written twice).
    frames_out (or null): the newest frames once more, compact (N,4,22), for the host path. */
 struct RecLoad { float4 v[6]; };
-__device__ __forceinline__ void obs_fetch(const Arrays &A, int step, uint32_t mask, int g, int64_t my_env, int lane, RecLoad &R)
+/* which record word lane `lane` fetches in round r: slot r*32 + lane in [buffer][env][float4] order, 168 used */
+__device__ __forceinline__ void fetch_slot(int r, int lane, int &k, int &e8, int &f)
+{
+    const int sl = r * 32 + lane;
+    k = sl / (OBS_ENVS * REC_F4);
+    const int rem = sl - k * (OBS_ENVS * REC_F4);
+    e8 = rem / REC_F4; f = rem - e8 * REC_F4;
+}
+__device__ __forceinline__ void obs_fetch(const Arrays &A, int step, uint32_t mask, int g, int my_env, int lane, RecLoad &R)
 {
     const uint32_t m8 = (mask >> (8 * g)) & 0xffu;
 #pragma unroll
     for (int r = 0; r < 6; r++) {
-        const int sl = r * 32 + lane;            /* slot in [buffer][env][float4] order, 168 used */
-        const int k = sl / (OBS_ENVS * REC_F4), rem = sl - k * (OBS_ENVS * REC_F4);
-        const int e8 = rem / REC_F4, f = rem - e8 * REC_F4;
-        const int64_t env = __shfl_sync(0xffffffffu, my_env, (8 * g + e8) & 31);
+        int k, e8, f;
+        fetch_slot(r, lane, k, e8, f);
+        const int env = __shfl_sync(0xffffffffu, my_env, (8 * g + e8) & 31);
         R.v[r] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (sl < 3 * OBS_ENVS * REC_F4 && ((m8 >> e8) & 1u)) {
+        if ((r < 5 || lane < 3 * OBS_ENVS * REC_F4 - 160) && ((m8 >> e8) & 1u)) {
             const int b = k == 0 ? buf_prev(step) : k == 1 ? buf_cur(step) : buf_next(step);
-            const float4 *p = A.pose[b] + env * POSE_F4 + f;
+            const float4 *p = A.pose[b] + (int64_t)env * POSE_F4 + f;
             R.v[r] = k == 2 ? __ldcg(p) : *p;
         }
     }
 }
 __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, float *obs_out, float *frames_out, int step, float *s_stage,
-                                         uint32_t mask, int64_t my_env, int lane)
+                                         uint32_t mask, int64_t my_env64, int lane)
 {
+    const int my_env = (int)my_env64; /* a handle holds fewer than 2^31 envs */
     const int a = lane & 3, el = lane >> 2;
     float4 *recs4 = reinterpret_cast<float4 *>(s_stage + BLOCK_WORDS);
     float2 *mine = reinterpret_cast<float2 *>(s_stage) + lane * 33; /* row (el, a) of the staged blocks */
@@ -234,18 +242,18 @@ __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, flo
         /* the staging areas are free: every lane has waited for its own bulk copies, then the warp synchronised */
 #pragma unroll
         for (int r = 0; r < 6; r++)
-            if (r * 32 + lane < 3 * OBS_ENVS * REC_F4) recs4[r * 32 + lane] = R.v[r];
+            if (r < 5 || lane < 3 * OBS_ENVS * REC_F4 - 160) recs4[r * 32 + lane] = R.v[r];
         __syncwarp();
         /* next group with work, its loads in flight from here on */
         int gn = g + 1;
         while (gn < 4 && ((mask >> (8 * gn)) & 0xffu) == 0u) gn++;
         if (gn < 4) obs_fetch(A, step, mask, gn, my_env, lane, R);
-        const int64_t env = __shfl_sync(0xffffffffu, my_env, 8 * g + el);
+        const int env = __shfl_sync(0xffffffffu, my_env, 8 * g + el);
         if ((m8 >> el) & 1u) {
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 float o[22];
-                frame_of_record(recs4 + (k * OBS_ENVS + el) * REC_F4, a, false, cfg, o);
+                frame_of_record(recs4 + (k * OBS_ENVS + el) * REC_F4, a, cfg, o);
 #pragma unroll
                 for (int i = 0; i < 11; i++) mine[k * 11 + i] = make_float2(o[2 * i], o[2 * i + 1]);
             }
@@ -253,7 +261,7 @@ __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, flo
         fence_async_smem();
         __syncwarp();
         if (a == 0 && ((m8 >> el) & 1u)) /* one lane per env */
-            bulk_store(obs_out + env * (4 * OBS), s_stage + el * (4 * OBS), 4 * OBS * sizeof(float));
+            bulk_store(obs_out + (int64_t)env * (4 * OBS), s_stage + el * (4 * OBS), 4 * OBS * sizeof(float));
         bulk_commit();
         if (frames_out != nullptr) {
             float2 *fr2 = reinterpret_cast<float2 *>(frames_out);
@@ -262,8 +270,8 @@ __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, flo
             for (int it = 0; it < 11; it++) { /* 8 x 4 x 11 = 352 float2: the third frame of every row */
                 const int idx = it * 32 + lane;
                 const int row = idx / 11, j = idx - row * 11;
-                const int64_t env2 = __shfl_sync(0xffffffffu, my_env, 8 * g + (row >> 2));
-                if ((m8 >> (row >> 2)) & 1u) fr2[env2 * 44 + (row & 3) * 11 + j] = stage2[row * 33 + 22 + j];
+                const int env2 = __shfl_sync(0xffffffffu, my_env, 8 * g + (row >> 2));
+                if ((m8 >> (row >> 2)) & 1u) fr2[(int64_t)env2 * 44 + (row & 3) * 11 + j] = stage2[row * 33 + 22 + j];
             }
         }
         bulk_wait_read();
@@ -323,6 +331,7 @@ __device__ __forceinline__ void flush_tally(const Tally &T, double *stats, int l
 {
     int nd = T.done, gb = T.goals_b, gr = T.goals_r, nc = T.contacts, ov = T.overflow, nf = T.nonfinite;
     float ret = T.ret;
+    if (!__any_sync(0xffffffffu, (nd | gb | gr | nc | ov | nf) != 0)) return; /* the common case of the streaming kernel */
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         nd += __shfl_xor_sync(0xffffffffu, nd, o); gb += __shfl_xor_sync(0xffffffffu, gb, o);
@@ -384,7 +393,10 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
 #define MSOC_LIGHT_BLOCK 64 /* small blocks: they slip into an SM as soon as one heavy block has left it */
 #endif
 constexpr int LIGHT_BLOCK = MSOC_LIGHT_BLOCK;
-constexpr int LIGHT_MIN_BLOCKS = 512 / LIGHT_BLOCK; /* 128 registers per thread */
+#ifndef MSOC_LIGHT_MIN_BLOCKS
+#define MSOC_LIGHT_MIN_BLOCKS 6 /* register cap 168: no spills; 8 (cap 128) spills and is slower */
+#endif
+constexpr int LIGHT_MIN_BLOCKS = MSOC_LIGHT_MIN_BLOCKS;
 constexpr size_t LIGHT_SMEM_BYTES = (size_t)(LIGHT_BLOCK / 32) * STAGE_WORDS * sizeof(float);
 __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light_kernel(const __grid_constant__ StepParams P)
 {

@@ -367,29 +367,29 @@ MSOC_HD void store_env(const Arrays &A, int buf, int64_t e, Env &E, bool score_d
 MSOC_HD void unit_mag(float dx, float dy, float &ux, float &uy, float &mag)
 {
     const float d2 = fmaf(dx, dx, dy * dy);
-    if (d2 > 1e-16f) { /* mag > 1e-8, game/game.py:281 */
-        const float inv = rsqrt_f(d2);
-        ux = dx * inv; uy = dy * inv; mag = d2 * inv * 0.001f; /* / hypot(800, 600) */
-    } else { ux = 0.0f; uy = 0.0f; mag = 0.0f; }
+    /* mag > 1e-8 (game/game.py:281), else all three are zero; d2 is never subnormal past the test, so the bare
+       hardware reciprocal square root (MUFU.RSQ) is what rsqrtf() returns */
+#if defined(__CUDA_ARCH__)
+    float inv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(d2));
+    inv = d2 > 1e-16f ? inv : 0.0f;
+#else
+    const float inv = d2 > 1e-16f ? 1.0f / sqrtf(d2) : 0.0f;
+#endif
+    ux = dx * inv; uy = dy * inv; mag = d2 * inv * 0.001f; /* / hypot(800, 600) */
 }
 
-MSOC_HD float4 ld_f4(const float4 *p, bool cg)
-{
-#if defined(__CUDA_ARCH__)
-    return cg ? __ldcg(p) : *p; /* cg: from L2 (records another lane of the warp has just written) */
-#else
-    (void)cg; return *p;
-#endif
-}
-/* Frame of agent a (22 floats) from an env record.  Scaled by reciprocals (within 1.5 ulp of the reference's
-   divisions).  u(p_j - p_i) = -u(p_i - p_j) exactly, so the four agents' frames are consistent with each other. */
-MSOC_HD void frame_of_record(const float4 *rec, int a, bool cg, const SimCfg &c, float *o)
+/* Frame of agent a (22 floats) from an env record (its first seven float4).  Scaled by reciprocals (within 1.5 ulp
+   of the reference's divisions).  u(p_j - p_i) = -u(p_i - p_j) exactly, so the four agents' frames are consistent
+   with each other. */
+MSOC_HD void frame_of_record(const float4 *rec, int a, const SimCfg &c, float *o)
 {
     const int opp = (a & 2) ^ 2;
-    const float4 own = ld_f4(rec + a, cg), mate = ld_f4(rec + (a ^ 1), cg), o0 = ld_f4(rec + opp, cg), o1 = ld_f4(rec + opp + 1, cg);
-    const float4 ball = ld_f4(rec + 4, cg), ang4 = ld_f4(rec + 5, cg), w4 = ld_f4(rec + 6, cg);
-    const float ang = a == 0 ? ang4.x : a == 1 ? ang4.y : a == 2 ? ang4.z : ang4.w;
-    const float w = a == 0 ? w4.x : a == 1 ? w4.y : a == 2 ? w4.z : w4.w;
+    const float4 own = rec[a];
+    const float2 *xy = reinterpret_cast<const float2 *>(rec); /* positions: float2 0, 2, 4, 6, 8 */
+    const float2 mate = xy[2 * (a ^ 1)], o0 = xy[2 * opp], o1 = xy[2 * opp + 2], ball = xy[8];
+    const float *fl = reinterpret_cast<const float *>(rec);
+    const float ang = fl[20 + a], w = fl[24 + a];
     o[0] = own.z * c.inv_vmax;
     o[1] = own.w * c.inv_vmax;
     o[2] = ang * 0.318309886183790672f;

@@ -85,7 +85,7 @@ static void write_obs(const HostSim *h, int64_t e, float *obs_out)
     const float4 *recs[3] = {h->A.pose[buf_prev(h->step)] + e * POSE_F4, h->A.pose[buf_cur(h->step)] + e * POSE_F4,
                              h->A.pose[buf_next(h->step)] + e * POSE_F4};
     for (int a = 0; a < 4; a++)
-        for (int k = 0; k < 3; k++) frame_of_record(recs[k], a, false, h->cfg, obs_out + a * OBS + k * FRAME);
+        for (int k = 0; k < 3; k++) frame_of_record(recs[k], a, h->cfg, obs_out + a * OBS + k * FRAME);
 }
 
 void hsim_reset(HostSim *h, const uint8_t *mask, int mode, int has_seed, uint64_t seed, float *obs_out)
