@@ -38,3 +38,23 @@ def _built_checkers():
     import hostsim_lib
     hostsim_lib.build()
     yield
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Parity margins observed in this run (tests/parity_util.py record()) -> JSON."""
+    import json
+    try:
+        import parity_util as P
+    except Exception:
+        return
+    if not P.REPORT:
+        return
+    path = os.environ.get("MSOC_PARITY_REPORT")
+    if path is None:
+        if not _has_cuda():
+            return
+        path = os.path.join(ROOT, "gpurun_out", "parity_report.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    bands = {"rtol": P.RTOL, "atol": P.ATOL, "max_over_fraction": P.MAX_OVER_FRACTION, "max_ratio": P.MAX_RATIO}
+    with open(path, "w") as f:
+        json.dump({"bands": bands, "checks": P.REPORT}, f, indent=1, sort_keys=True)

@@ -30,6 +30,24 @@ ATOL = {
 }
 
 CONFIG = O.DEFAULT_CONFIG
+# every key the reference reads moved off its shipped value (readers: soccer_env.py:63-64, game/game.py:264,330,368,
+# 430; game/entities.py:11-17,62-67): explicit force / angular-velocity scales, no proximity shaping (the prox == 0
+# branch), a conceded-goal penalty, a non-zero terminal bonus, a short episode
+ALT_CONFIG = {
+    "physics": {"max_velocity": 160, "agent_mass": 8, "ball_mass": 1.5, "agent_friction": 0.985, "ball_friction": 0.96,
+                "action_torque_max": 1500.0, "action_force_max": 90000.0, "max_angular_velocity": 12.0},
+    "rewards": {"kick_possession_reward": 0.0, "ball_proximity_multiplier": 0.0, "move_ball_to_goal_multiplier": 0.25,
+                "alive_penalty": 0.0005, "goal_scored_reward": 2.5, "goal_conceded_penalty": 1.5,
+                "score_difference_multiplier": 5.0},
+    "simulation": {"max_steps": 37},
+}
+# the reference's fall-backs when keys are absent (soccer_env.py:63-64): action_torque_max 100000 spins an agent by
+# ~27 rad per step -- several turns, the full-range angle reduction of the kernels
+SPIN_CONFIG = {
+    "physics": {"max_velocity": 200, "agent_mass": 10, "ball_mass": 1, "agent_friction": 0.99, "ball_friction": 0.97},
+    "rewards": dict(O.DEFAULT_CONFIG["rewards"]),
+    "simulation": {"max_steps": 1000},
+}
 
 
 def wrap(a):
@@ -119,7 +137,7 @@ def f32(x):
     return np.asarray(x, np.float32).astype(np.float64)
 
 
-def random_state(rng: np.random.Generator, kind: str = "open") -> dict:
+def random_state(rng: np.random.Generator, kind: str = "open", config=None) -> dict:
     """One fp32-representable env state.  kind: 'open' (SURVEY section 8d config-2 recipe: uniform over the
     field box, velocities in the disc <= 200, angles U(-pi,pi), ang-vel U(-10,10), steps U{0..998}),
     'walls' (agents and ball hugging walls / corners / goal mouths), 'scrum' (bodies packed around the
@@ -185,7 +203,7 @@ def random_state(rng: np.random.Generator, kind: str = "open") -> dict:
         "vbias": np.zeros((5, 2)), "wbias": np.zeros(5),
         "steps": int(rng.integers(0, 999)), "score": (int(rng.integers(0, 3)), int(rng.integers(0, 3))),
         "mode": int(rng.integers(0, 3)), "spawn_count": int(rng.integers(0, 5)), "seed": int(rng.integers(0, 2**31)),
-        "hist": hist, "obs": obs_of_hist(hist), "cache": [],
+        "hist": hist, "obs": obs_of_hist(hist, config), "cache": [],
     }
     return d
 
@@ -308,13 +326,44 @@ def compare_all(sim, ora, obs_d, obs_o, rew_d, rew_o, n, label="", skip=None):
     return worst, failing, cache_bad
 
 
-def check_single_step(sim_cls, n: int, seed: int, **kw):
+# ------------------------------------------------------------------------------------ margins report
+REPORT = {}
+
+
+def record(name: str, entry: dict) -> None:
+    """Collects the observed parity margins of the run; written by tests/conftest.py at session end to
+    $MSOC_PARITY_REPORT (default gpurun_out/parity_report.json when a GPU is present)."""
+    REPORT[name] = entry
+
+
+def summarize(failing, worst, n, events=None) -> dict:
+    over = {}
+    for _, d in failing:
+        for k, v in d.items():
+            over[k] = over.get(k, 0) + 1
+    e = {"envs": n, "worst_violation_ratio": {k: round(float(v), 3) for k, v in worst.items()},
+         "envs_over_band": len(failing), "over_band_by_quantity": over}
+    if events:
+        e["events"] = events
+    return e
+
+
+# what the asserts allow beyond the per-quantity band |a-b| <= atol + 1e-5 |b|, set from the recorded margins
+# (profiles/r02_parity.json) plus headroom: multi-contact Gauss-Seidel solves on the injected deep-overlap states
+# amplify fp32 rounding a little
+MAX_OVER_FRACTION = 1 / 500   # of the envs of a check may leave a band (observed on the B200: 3 and 5 of 4 096, all scrums) ...
+MAX_RATIO = 4.0               # ... and none by more than this factor (observed: 1.97 and 3.00)
+MAX_TRACKED_FRACTION = 1 / 4000  # of the (env, step) pairs of a tracked rollout (observed: 0 of 27 000)
+
+
+def check_single_step(sim_cls, n: int, seed: int, config=None, name=None, **kw):
     """Inject n seeded states (all four scenario kinds) into both sides, one step with out-of-range
     actions (clipping is exercised), compare everything."""
+    config = CONFIG if config is None else config
     rng = np.random.default_rng(seed)
-    sim = sim_cls(n, CONFIG, seed=0, **kw)
-    ora = O.OracleVec(n, CONFIG, seed=0)
-    states = [random_state(rng, KINDS[i % 4]) for i in range(n)]
+    sim = sim_cls(n, config, seed=0, **kw)
+    ora = O.OracleVec(n, config, seed=0)
+    states = [random_state(rng, KINDS[i % 4], config) for i in range(n)]
     inject(sim, ora, states)
     edge = goal_knife_edge(states)
     assert edge.sum() <= max(1, n // 2000), f"{edge.sum()} knife-edge goal cases among {n} envs"
@@ -326,31 +375,37 @@ def check_single_step(sim_cls, n: int, seed: int, **kw):
     assert np.array_equal(r_d[:, 0], r_d[:, 1]), "blue rewards must be identical (game/game.py:324-375)"
     worst, failing, cache_bad = compare_all(sim, ora, o_d, o_o, r_d, r_o, n, skip=edge)
     assert not cache_bad, f"arbiter cache / counters differ for envs {cache_bad[:10]}"
-    # Multi-contact Gauss-Seidel solves on the injected deep-overlap states amplify fp32 rounding a little
-    # beyond the per-quantity band: allow <= 0.5 % of the envs to exceed it, and none by more than 5x.
-    assert len(failing) <= max(1, n // 200), f"{len(failing)} envs out of tolerance, e.g. {failing[:5]}; worst {worst}"
-    assert max(worst.values()) < 5.0, worst
+    if name:
+        by_kind = {}
+        for i, d in failing:
+            by_kind[KINDS[i % 4]] = by_kind.get(KINDS[i % 4], 0) + 1
+        e = summarize(failing, worst, n, {"goals": int(np.abs(g_o).sum()), "knife_edge_goal_cases_excluded": int(edge.sum())})
+        e["over_band_by_scenario_kind"] = by_kind
+        record(name, e)
+    assert len(failing) <= max(1, int(n * MAX_OVER_FRACTION)), f"{len(failing)} envs out of tolerance, e.g. {failing[:5]}; worst {worst}"
+    assert max(worst.values()) < MAX_RATIO, worst
     return worst, int(np.abs(g_o).sum())
 
 
-def check_tracked_rollout(sim_cls, n: int, steps: int, seed: int, mode: int = 2, **kw):
+def check_tracked_rollout(sim_cls, n: int, steps: int, seed: int, mode: int = 2, config=None, name=None, **kw):
     """`steps`-step rollout from a shared reset; after every step the oracle is re-synchronised to the
     device state, so each of the steps is an independent single-step parity check on states the sim
     itself reaches (spawn overlap with walls, resting contacts, warm-started arbiters, goals, truncation,
     auto-reset).  Returns the number of (env, step) pairs that were out of tolerance and the total."""
+    config = CONFIG if config is None else config
     rng = np.random.default_rng(seed)
-    sim = sim_cls(n, CONFIG, seed=seed, **kw)
-    ora = O.OracleVec(n, CONFIG, seed=seed)
+    sim = sim_cls(n, config, seed=seed, **kw)
+    ora = O.OracleVec(n, config, seed=seed)
     o_d = sim.reset(mode, seed=seed)
     o_o = ora.reset(mode, seed=seed)
     assert np.allclose(o_d, o_o, atol=ATOL["obs"]), "reset observations differ"
     # start late in the episode for half of the envs so that truncation + auto-reset are exercised
     st = sim.get_states(np.arange(n))
     for i in range(0, n, 2):
-        st[i].steps = CONFIG["simulation"]["max_steps"] - 1 - (i % max(steps, 1))
+        st[i].steps = max(0, config["simulation"]["max_steps"] - 1 - (i % max(steps, 1)))
     sim.set_states(np.arange(n), st)
     out_of_tol, total, events = 0, 0, {"goals": 0, "dones": 0, "contacts": 0}
-    worst_all = {}
+    worst_all, all_failing = {}, []
     for t in range(steps):
         dev_states = sim.get_states(np.arange(n))
         synced = [dev_to_oracle_state(dev_states[i], o_d[i]) for i in range(n)]
@@ -370,4 +425,9 @@ def check_tracked_rollout(sim_cls, n: int, steps: int, seed: int, mode: int = 2,
         events["contacts"] += sum(1 for i in range(n) if ora.env(i).contact_count() > 0)
         for k, v in worst.items():
             worst_all[k] = max(worst_all.get(k, 0.0), v)
+        all_failing += failing
+    if name:
+        e = summarize(all_failing, worst_all, total, events)
+        e["env_steps_compared"] = e.pop("envs")
+        record(name, e)
     return out_of_tol, total, events, worst_all

@@ -69,13 +69,13 @@ def test_api_surface(kind):
     assert soccer_env.make_env(_sim_factory=FACTORIES[kind]).possible_agents == AGENTS
 
 
-def test_constructor_and_step_errors():
+def test_constructor_and_step_errors(kind="hostsim"):
     with pytest.raises(ValueError):
-        soccer_env.SoccerEnv(env=2, _sim_factory=B.HostSimBacked)
+        soccer_env.SoccerEnv(env=2, _sim_factory=FACTORIES[kind])
     with pytest.raises(ValueError):
-        soccer_env.SoccerEnv(num_envs=8, _sim_factory=B.HostSimBacked)
-    soccer_env.SoccerEnv(num_envs=1, env=1, _sim_factory=B.HostSimBacked)  # allowed values are ignored
-    env = make_env()
+        soccer_env.SoccerEnv(num_envs=8, _sim_factory=FACTORIES[kind])
+    soccer_env.SoccerEnv(num_envs=1, env=1, _sim_factory=FACTORIES[kind])  # allowed values are ignored
+    env = make_env(kind)
     env.reset()
     with pytest.raises(ValueError, match="Missing actions"):
         env.step({a: [0, 0, 0] for a in AGENTS[:3]})
@@ -87,8 +87,8 @@ def test_constructor_and_step_errors():
         env.step({**zero(), "agent_2": [0.0, float("nan"), 0.0]})
 
 
-def test_reset_options_and_seed_determinism():
-    env = make_env()
+def test_reset_options_and_seed_determinism(kind="hostsim"):
+    env = make_env(kind)
     o1, _ = env.reset(seed=11, options={"use_full_random_positions": True})
     o2, _ = env.reset(seed=11, options={"use_full_random_positions": True})
     o3, _ = env.reset(seed=12, options={"use_full_random_positions": True})
@@ -97,9 +97,9 @@ def test_reset_options_and_seed_determinism():
     assert np.allclose(latest(of["agent_0"])[4:7], [0.0, 1.0, 0.198], atol=1e-6)
 
 
-def test_truncation_clears_agents_and_reports_terminal_reward():
+def test_truncation_clears_agents_and_reports_terminal_reward(kind="hostsim"):
     cfg = {**P.CONFIG, "rewards": {**P.CONFIG["rewards"], "score_difference_multiplier": 5.0}, "simulation": {"max_steps": 4}}
-    env = make_env(config=cfg)
+    env = make_env(kind, config=cfg)
     env.reset(seed=1)
     for t in range(4):
         obs, rew, term, trunc, infos = env.step(zero())
@@ -231,10 +231,10 @@ def test_own_goal_is_penalised_by_shaping(kind):
 
 
 # ------------------------------------------------------------------------------ vec env
-def test_vec_env_contract():
+def test_vec_env_contract(kind="hostsim"):
     n = 6
     cfg = {**P.CONFIG, "simulation": {"max_steps": 5}}
-    vec = marl_vecenv.SyncMultiAgentVecEnv([lambda: make_env(config=cfg)] * n, seed=7, _sim_factory=B.HostSimBacked)
+    vec = marl_vecenv.SyncMultiAgentVecEnv([lambda: make_env(kind, config=cfg)] * n, seed=7, _sim_factory=FACTORIES[kind])
     assert vec.num_envs == n and len(vec.envs) == n and vec.possible_agents == AGENTS
     assert vec.single_observation_space.shape == (66,) and vec.single_action_space.shape == (3,)
     obs = vec.reset(seed=1)
@@ -261,13 +261,13 @@ def test_vec_env_contract():
     vec.close()
 
 
-def test_vec_env_matches_single_envs_on_shared_actions():
+def test_vec_env_matches_single_envs_on_shared_actions(kind="hostsim"):
     """SyncMultiAgentVecEnv == the per-env loop of the reference (marl_vecenv.py:39-53) when the per-env
     states are the same: run the batched sim and n single-env sims from identical injected states."""
     n = 5
-    vec = marl_vecenv.SyncMultiAgentVecEnv(None, num_envs=n, config=P.CONFIG, seed=3, _sim_factory=B.HostSimBacked)
+    vec = marl_vecenv.SyncMultiAgentVecEnv(None, num_envs=n, config=P.CONFIG, seed=3, _sim_factory=FACTORIES[kind])
     vec.reset(seed=40, options={"use_full_random_positions": True})
-    singles = [make_env(seed=3) for _ in range(n)]
+    singles = [make_env(kind, seed=3) for _ in range(n)]
     for i, e in enumerate(singles):
         e.reset()
         e._sim.set_state(0, vec._sim.get_state(i))  # the history poses travel in the state

@@ -54,9 +54,9 @@ def _check(sim_cls, gold):
     """Step 1 from the injected start states, step 2 from the golden state after step 1 (its arbiter cache, bias
     velocities and observation history included): each is an independent check against the file."""
     z, n = gold["z"], len(gold["s0"])
-    for first, act, obs, rew, done, goal, want in (
+    for k, (first, act, obs, rew, done, goal, want) in enumerate((
             (gold["s0"], z["act1"], z["obs1"], z["rew1"], z["done1"], z["goal1"], gold["s1"]),
-            (gold["s1"], z["act2"], z["obs2"], z["rew2"], z["done2"], z["goal2"], gold["s2"])):
+            (gold["s1"], z["act2"], z["obs2"], z["rew2"], z["done2"], z["goal2"], gold["s2"]))):
         sim = sim_cls(n, P.CONFIG, seed=0)
         sim.set_states(np.arange(n), [P.oracle_to_dev_state(s) for s in first])
         o_d, r_d, d_d, g_d = sim.step(act, auto_reset=False)
@@ -64,8 +64,9 @@ def _check(sim_cls, gold):
         assert np.array_equal(g_d, goal), "goal flags differ from the golden vectors"
         worst, failing, cache_bad = P.compare_all(sim, _GoldenOracle(want), o_d, obs, r_d, rew, n)
         assert not cache_bad, f"arbiter cache / counters differ for envs {cache_bad[:10]}"
-        assert len(failing) <= max(1, n // 200), f"{len(failing)} envs out of tolerance, e.g. {failing[:5]}; worst {worst}"
-        assert max(worst.values()) < 5.0, worst
+        P.record(f"golden/{getattr(sim_cls, '__name__', 'sim')}/step{k + 1}", P.summarize(failing, worst, n))
+        assert len(failing) <= max(1, int(n * P.MAX_OVER_FRACTION)), f"{len(failing)} envs out of tolerance, e.g. {failing[:5]}; worst {worst}"
+        assert max(worst.values()) < P.MAX_RATIO, worst
 
 
 def test_host_build_of_the_kernel_arithmetic_matches_the_golden_vectors(gold):

@@ -30,21 +30,50 @@ def test_spawn_bit_exact_all_modes():
 
 def test_single_step_injected_states_4096():
     """BASELINE config 2: 4 096 batched envs, parity vs the restated Game on injected states."""
-    worst, goals = P.check_single_step(Dev, 4096, seed=11)
+    worst, goals = P.check_single_step(Dev, 4096, seed=11, name="cuda/single_step_4096")
     assert goals > 200
     print("worst violation ratios", worst)
 
 
+def test_single_step_non_default_config_4096():
+    """Every config key moved (P.ALT_CONFIG): explicit force / angular-velocity scales, the prox == 0 branch, a conceded
+    penalty, a terminal bonus, max_steps 37 (readers: soccer_env.py:63-64, game/game.py:264,330,368,430)."""
+    worst, goals = P.check_single_step(Dev, 4096, seed=12, config=P.ALT_CONFIG, name="cuda/single_step_alt_config_4096")
+    assert goals > 100
+
+
+def test_tracked_rollout_non_default_config():
+    bad, total, ev, worst = P.check_tracked_rollout(Dev, 96, 80, seed=6, mode=O.MODE_FULL_RANDOM, config=P.ALT_CONFIG,
+                                                    name="cuda/tracked_alt_config")
+    assert ev["dones"] >= 96 and ev["contacts"] > 500
+    assert bad <= total * P.MAX_TRACKED_FRACTION, (bad, total, worst)
+
+
+def test_high_torque_fallback_config_keeps_angles_wrapped():
+    """config without action_torque_max: the reference's fall-back of 100000 (soccer_env.py:64) spins the agents by
+    several turns per step; the kernels' angle stays wrapped and the observation's angle feature stays in [-1, 1]."""
+    bad, total, ev, worst = P.check_tracked_rollout(Dev, 64, 40, seed=8, mode=O.MODE_RANDOM, config=P.SPIN_CONFIG,
+                                                    name="cuda/tracked_high_torque")
+    assert bad <= total * P.MAX_TRACKED_FRACTION, (bad, total, worst)
+    sim = Dev(256, P.SPIN_CONFIG, seed=1)
+    sim.reset(O.MODE_FIXED)
+    for t in range(30):
+        o, *_ = sim.step(np.ones((256, 4, 3), np.float32), auto_reset=False)
+        ang = o.reshape(256, 4, 3, 22)[:, :, 2, 2]
+        assert np.all(np.abs(ang) <= 1.0 + 1e-6), float(np.abs(ang).max())
+    assert all(sim.get_state(0).angvel[i] > 400.0 for i in range(4))  # > 2 pi per step
+
+
 def test_tracked_rollout_full_random_100_steps():
-    bad, total, ev, worst = P.check_tracked_rollout(Dev, 128, 100, seed=3, mode=O.MODE_FULL_RANDOM)
+    bad, total, ev, worst = P.check_tracked_rollout(Dev, 128, 100, seed=3, mode=O.MODE_FULL_RANDOM, name="cuda/tracked_full_random")
     assert ev["dones"] > 0 and ev["contacts"] > 1000
-    assert bad <= total // 1000 + 1, (bad, total, worst)
+    assert bad <= total * P.MAX_TRACKED_FRACTION, (bad, total, worst)
     print("tracked rollout", bad, total, ev, worst)
 
 
 def test_tracked_rollout_default_mode():
-    bad, total, ev, worst = P.check_tracked_rollout(Dev, 64, 60, seed=4, mode=O.MODE_RANDOM)
-    assert bad <= total // 1000 + 1, (bad, total, worst)
+    bad, total, ev, worst = P.check_tracked_rollout(Dev, 64, 60, seed=4, mode=O.MODE_RANDOM, name="cuda/tracked_default_mode")
+    assert bad <= total * P.MAX_TRACKED_FRACTION, (bad, total, worst)
 
 
 def test_free_running_contact_free_100_steps():
@@ -61,7 +90,42 @@ def test_free_running_contact_free_100_steps():
         assert np.array_equal(d_d, d_o) and np.array_equal(g_d, g_o)
     worst, failing, cache_bad = P.compare_all(sim, ora, o_d, o_o, r_d, r_o, n)
     assert not cache_bad
-    assert max(worst.values()) < 8.0, worst
+    P.record("cuda/free_running_contact_free_100_steps", P.summarize(failing, worst, n))
+    assert max(worst.values()) < 1.0, worst  # observed on the B200: 0.17
+
+
+def test_free_running_through_contacts_divergence_curve():
+    """North star: "100-step rollouts from shared states".  Through contacts fp32 and fp64 trajectories separate
+    chaotically (a contact one step earlier or later), so beyond the first steps this cannot be an assertion about
+    every env: the test MEASURES it -- fraction of envs with every quantity inside the single-step band, and goal /
+    done flag mismatches, after k = 1, 10, 30, 100 free-running steps of 4 096 envs from one shared full-random reset
+    (corner spawns: a quarter of the envs start in contact) -- records the curve in the parity report and asserts
+    what must hold: done flags always (a pure step count), the first step inside the band for (almost) all envs, and
+    a majority still inside after 100 steps."""
+    n = 4096
+    sim = Dev(n, P.CONFIG, seed=31)
+    ora = O.OracleVec(n, P.CONFIG, seed=31)
+    sim.reset(O.MODE_FULL_RANDOM, seed=6)
+    ora.reset(O.MODE_FULL_RANDOM, seed=6)
+    rng = np.random.default_rng(9)
+    curve = {}
+    goal_mismatch = 0
+    for t in range(1, 101):
+        act = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)
+        o_d, r_d, d_d, g_d = sim.step(act, auto_reset=False)
+        o_o, r_o, d_o, g_o = ora.step(act, auto_reset=False, nthreads=8)
+        assert np.array_equal(d_d, d_o)
+        goal_mismatch += int((g_d != g_o).sum())
+        if t in (1, 10, 30, 100):
+            worst, failing, cache_bad = P.compare_all(sim, ora, o_d, o_o, r_d, r_o, n)
+            bad = {i for i, _ in failing} | set(cache_bad)
+            curve[t] = {"fraction_in_band": round(1.0 - len(bad) / n, 4), "cache_structure_mismatches": len(set(cache_bad)),
+                        "goal_flag_mismatches_so_far": goal_mismatch,
+                        "median_worst_ratio_of_out_of_band_envs": round(float(np.median([max(d.values()) for _, d in failing])), 1) if failing else 0.0}
+    P.record("cuda/free_running_through_contacts_4096", {"envs": n, "curve": curve})
+    print("free-running divergence curve", curve)
+    assert curve[1]["fraction_in_band"] >= 0.995
+    assert curve[100]["fraction_in_band"] >= 0.5
 
 
 def test_global_offset_shards_agree():
