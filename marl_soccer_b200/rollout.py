@@ -101,38 +101,113 @@ class RolloutBuffer:
         self.values = torch.zeros((T, N, 2), device=device)
 
 
+def _policy_step(agent, x, policy_dtype):
+    if policy_dtype is not None:
+        with torch.autocast(device_type="cuda", dtype=policy_dtype):
+            action, logprob, _, value = agent.get_action_and_value(x)
+        return action.float(), logprob.float(), value.float()
+    action, logprob, _, value = agent.get_action_and_value(x)
+    return action, logprob, value
+
+
 @torch.no_grad()
 def collect_rollout(sim, agent: Agent, normalizer: RunningMeanStd, buf: RolloutBuffer, next_obs: torch.Tensor,
-                    next_done: torch.Tensor, generator=None, update_normalizer: bool = True, policy_dtype=None):
+                    next_done: torch.Tensor, generator=None, update_normalizer: bool = True, policy_dtype=None,
+                    deterministic: bool = False):
     """One rollout of `buf.obs.shape[0]` steps (marl-soccer.ipynb:366-431): blue = policy, red = U(-1, 1).
-    next_obs: (N, 2, 66) raw observations of the blue agents; next_done: (N, 2).  Returns the updated pair.
-    policy_dtype: optional autocast dtype for the MLPs (e.g. torch.bfloat16); the simulator is always fp32."""
+    next_obs: (N, 2, 66) raw observations of the blue agents (may be a view of the simulator's observation buffer: it is
+    consumed before the next step overwrites it); next_done: (N, 2).  Returns the updated pair (next_obs is a view of
+    sim.obs).  policy_dtype: optional autocast dtype for the MLPs (e.g. torch.bfloat16); the simulator is always fp32.
+    deterministic: blue plays the policy mean and red stands still (eval.py:84-104 style; used by the parity test)."""
     T = buf.obs.shape[0]
     n = sim.num_envs
-    dev = sim.device
     full = sim.actions  # (N, 4, 3) device buffer of the handle
+    mean32, inv_std32 = normalizer.mean.float(), 1.0 / (normalizer.std.float() + 1e-8)  # fp32 on the hot loop
     for t in range(T):
         buf.obs[t] = next_obs
         buf.dones[t] = next_done
-        x = normalizer.normalize(next_obs.reshape(-1, 66))
-        if policy_dtype is not None:
-            with torch.autocast(device_type="cuda", dtype=policy_dtype):
-                action, logprob, _, value = agent.get_action_and_value(x)
-            action, logprob, value = action.float(), logprob.float(), value.float()
+        x = torch.clamp((next_obs.reshape(-1, 66) - mean32) * inv_std32, -10.0, 10.0)
+        if deterministic:
+            action = agent.get_deterministic_action(x)
+            logprob, value = torch.zeros(x.shape[0], device=x.device), agent.get_value(x)
         else:
-            action, logprob, _, value = agent.get_action_and_value(x)
+            action, logprob, value = _policy_step(agent, x, policy_dtype)
         buf.values[t] = value.reshape(n, 2)
         buf.actions[t] = action.reshape(n, 2, 3)
         buf.logprobs[t] = logprob.reshape(n, 2)
         full[:, :2] = buf.actions[t]
-        full[:, 2:].uniform_(-1.0, 1.0, generator=generator)
+        if deterministic:
+            full[:, 2:] = 0.0
+        else:
+            full[:, 2:].uniform_(-1.0, 1.0, generator=generator)
         obs, reward, done, _goal = sim.step(full, auto_reset=True)
         buf.rewards[t] = reward
-        next_obs = obs[:, :2].clone()
+        next_obs = obs[:, :2]  # a view: read by the next iteration (or the caller) before the simulator steps again
         next_done = done.to(torch.float32)[:, None].expand(n, 2)
     if update_normalizer:
         normalizer.update(buf.obs.reshape(-1, 66))
     return next_obs, next_done
+
+
+class GraphedRollout:
+    """collect_rollout as ONE CUDA graph per rollout: the T steps (normalise -> MLPs -> sample -> red actions ->
+    msoc_step's three kernels -> storage) are captured once and replayed, so the ~40 launches per step cost no host
+    time and the simulator is never waiting for Python.  The simulator's step counter lives in device memory, which
+    is what makes a captured sequence of steps replayable (include/msoc.h).  Sampling uses torch's default CUDA
+    generator (graph-safe)."""
+
+    def __init__(self, sim, agent: Agent, normalizer: RunningMeanStd, buf: RolloutBuffer, policy_dtype=None,
+                 update_normalizer: bool = True):
+        self.sim, self.agent, self.normalizer, self.buf = sim, agent, normalizer, buf
+        self.policy_dtype, self.update_normalizer = policy_dtype, update_normalizer
+        dev = sim.device
+        self.mean32 = torch.zeros((66,), device=dev)
+        self.inv_std32 = torch.ones((66,), device=dev)
+        self.next_done = torch.zeros((sim.num_envs, 2), device=dev)
+        self.graph = None
+
+    def _refresh(self):
+        self.mean32.copy_(self.normalizer.mean.float())
+        self.inv_std32.copy_(1.0 / (self.normalizer.std.float() + 1e-8))
+
+    @torch.no_grad()
+    def _body(self):
+        sim, buf, n = self.sim, self.buf, self.sim.num_envs
+        full = sim.actions
+        for t in range(buf.obs.shape[0]):
+            cur = sim.obs[:, :2]  # the blue agents' rows of the simulator's own buffer: no clone
+            buf.obs[t] = cur
+            buf.dones[t] = self.next_done
+            x = torch.clamp((cur.reshape(-1, 66) - self.mean32) * self.inv_std32, -10.0, 10.0)
+            action, logprob, value = _policy_step(self.agent, x, self.policy_dtype)
+            buf.values[t] = value.reshape(n, 2)
+            buf.actions[t] = action.reshape(n, 2, 3)
+            buf.logprobs[t] = logprob.reshape(n, 2)
+            full[:, :2] = buf.actions[t]
+            full[:, 2:].uniform_(-1.0, 1.0)
+            _obs, reward, done, _goal = sim.step(full, auto_reset=True)
+            buf.rewards[t] = reward
+            self.next_done.copy_(done.to(torch.float32)[:, None].expand(n, 2))
+
+    def run(self):
+        """One rollout; returns (next_obs view, next_done)."""
+        self._refresh()
+        dev = self.sim.device
+        if self.graph is None:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._body()  # eager warm-up on the capture stream (cuBLAS workspaces, autocast caches)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._body()
+        else:
+            self.graph.replay()
+        if self.update_normalizer:
+            self.normalizer.update(self.buf.obs.reshape(-1, 66))
+        return self.sim.obs[:, :2], self.next_done
 
 
 @torch.no_grad()

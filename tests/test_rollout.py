@@ -110,3 +110,83 @@ def test_rollout_loop_on_the_device():
     assert float(red.min()) >= -1.0 and float(red.max()) <= 1.0 and abs(float(red.mean())) < 0.02
     adv, ret = compute_gae(agent, rms, buf, next_obs, next_done)
     assert adv.shape == (T, n, 2) and torch.isfinite(adv).all() and torch.isfinite(ret).all()
+
+
+@pytest.mark.gpu
+def test_deterministic_rollout_matches_the_same_loop_over_the_oracle():
+    """The rollout half against the oracle: 256 envs from the fixed kick-off (contact-free for the 8 steps), blue plays
+    the policy MEAN on normalised observations, red stands still; the same loop written out over the CPU oracle with the
+    same weights must produce the same observations, rewards and values step by step (fp32 GPU matmuls vs fp32 CPU
+    matmuls feed slightly different forces into two simulators: a few fp32 ulps on the observations)."""
+    import oracle_lib as O
+    import parity_util as P
+    from marl_soccer_b200.sim import BatchedSoccerSim
+    dev = torch.device("cuda:0")
+    n, T = 256, 8
+    torch.manual_seed(4)
+    agent = Agent()
+    rms = RunningMeanStd((66,), "cpu")
+    rms.mean = torch.linspace(-0.3, 0.3, 66, dtype=torch.float64)
+    rms.var = torch.linspace(0.5, 2.0, 66, dtype=torch.float64)
+    # --- device: collect_rollout over the CUDA simulator
+    sim = BatchedSoccerSim(n, config=P.CONFIG, device=dev, seed=3)
+    agent_d = Agent().to(dev)
+    agent_d.load_state_dict(agent.state_dict())
+    rms_d = RunningMeanStd((66,), dev)
+    rms_d.mean, rms_d.var = rms.mean.to(dev), rms.var.to(dev)
+    buf = RolloutBuffer(T, n, dev)
+    obs = sim.reset(O.MODE_FIXED, seed=5)[:, :2]
+    done = torch.zeros((n, 2), device=dev)
+    nxt, _ = collect_rollout(sim, agent_d, rms_d, buf, obs, done, update_normalizer=False, deterministic=True)
+    # --- oracle: the same loop, plain
+    ora = O.OracleVec(n, P.CONFIG, seed=3)
+    o = ora.reset(O.MODE_FIXED, seed=5)
+    for t in range(T):
+        blue = torch.from_numpy(o[:, :2].copy())
+        assert np.allclose(buf.obs[t].cpu().numpy(), blue.numpy(), atol=2e-4), t
+        with torch.no_grad():
+            x = rms.normalize(blue.reshape(-1, 66))
+            act = agent.get_deterministic_action(x).reshape(n, 2, 3)
+            val = agent.get_value(x).reshape(n, 2)
+        assert np.allclose(buf.values[t].cpu().numpy(), val.numpy(), atol=2e-3), t
+        assert np.allclose(buf.actions[t].cpu().numpy(), act.numpy(), atol=2e-4), t
+        full = np.zeros((n, 4, 3), np.float32)
+        full[:, :2] = act.numpy()
+        o, r, d, g = ora.step(full, auto_reset=True)
+        assert not d.any() and not g.any()
+        assert np.allclose(buf.rewards[t].cpu().numpy(), r, atol=1e-5), t
+    assert np.allclose(nxt.cpu().numpy(), o[:, :2], atol=2e-4)
+
+
+@pytest.mark.gpu
+def test_graphed_rollout_runs_the_whole_rollout_as_one_cuda_graph():
+    """GraphedRollout: the first run is eager and captures; replays step the simulator exactly T times each (the
+    device-side step counter keeps the captured sequence replayable for odd T too) and fill the buffers."""
+    import parity_util as P
+    from marl_soccer_b200.rollout import GraphedRollout
+    from marl_soccer_b200.sim import BatchedSoccerSim
+    dev = torch.device("cuda:0")
+    n, T = 2048, 7
+    cfg = dict(P.CONFIG)
+    cfg["simulation"] = {"max_steps": 10}
+    sim = BatchedSoccerSim(n, config=cfg, device=dev, seed=3)
+    torch.manual_seed(0)
+    agent = Agent().to(dev)
+    rms = RunningMeanStd((66,), dev)
+    buf = RolloutBuffer(T, n, dev)
+    sim.reset(2, seed=5)
+    sim.stats(reset=True)
+    ro = GraphedRollout(sim, agent, rms, buf)
+    for k in range(4):
+        prev = sim.obs.clone()
+        nxt, nd = ro.run()
+        torch.cuda.synchronize()
+        assert torch.equal(buf.obs[0], prev[:, :2])   # the rollout started from the observation the last one ended on
+        assert torch.isfinite(buf.rewards).all() and torch.isfinite(buf.values).all()
+    st = sim.stats()
+    assert st["env_steps"] == 4 * T * n and st["episodes"] == n * (4 * T // 10)
+    # frames shift consistently across the replays: the history really is the previous steps' frames
+    o4 = sim.obs.view(n, 4, 3, 22)
+    keep = ~sim.done.bool()
+    last_blue = buf.obs[T - 1].view(n, 2, 3, 22)
+    assert torch.equal(o4[keep][:, :2, 1], last_blue[keep][:, :, 2])
