@@ -66,6 +66,7 @@ struct msoc_handle {
     SimCfg cfg;
     Arrays A;
     int sm_count, blocks_per_sm, light_blocks_per_sm; /* persistent grids of the contact and light kernels */
+    int heavy_lanes_override; /* MSOC_HEAVY_LANES (experiments): 0 = choose by batch size */
     void *slab;
     /* internal I/O buffers of the host-buffer API */
     float *d_obs, *d_act, *d_rew;
@@ -112,6 +113,7 @@ struct StepParams {
     int64_t e0, e1;       /* the envs this launch steps */
     uint64_t global_offset;
     uint32_t flags;
+    int heavy_lanes;      /* envs per warp-batch of the heavy contact kernel: 32, 16 or 8 (launch_step) */
     int chunk;            /* -1: a whole step (list counters alternate with the step counter, the contact kernel advances it);
                              >= 0: one pipeline chunk of a host-buffer step (its own pre-zeroed counters, nobody advances) */
 };
@@ -449,6 +451,8 @@ constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
 #define MSOC_HEAVY_MIN_BLOCKS 5 /* register cap 204 */
 #endif
 constexpr int HEAVY_MIN_BLOCKS = MSOC_HEAVY_MIN_BLOCKS;
+
+constexpr int64_t HEAVY_FULL_WARP_ENVS = 393216; /* ranges of at least this many envs use full-warp heavy batches */
 constexpr int HEAVY_WARP_WORDS = (32 * ENV_STRIDE + 3) & ~3; /* 16-byte aligned per-warp scratch */
 constexpr size_t STEP_SMEM_BYTES = (size_t)(HEAVY_BLOCK / 32) * HEAVY_WARP_WORDS * sizeof(float);
 
@@ -463,7 +467,7 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
     /* this step's fast kernel is complete and the next one starts after this kernel: advance the step counter */
     if (P.chunk < 0 && blockIdx.x == 0 && tid == 0) P.ctl[CTL_STEP_FAST] = (step + 1) % 6;
     const int n_heavy = ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
-    const int heavy_batches = (n_heavy + 31) / 32;
+    const int heavy_batches = (n_heavy + P.heavy_lanes - 1) / P.heavy_lanes;
 
     Tally T; tally_clear(T);
     float ovf_store[MAXC - CON_FAST][CON_FIELDS]; /* local memory, touched only by envs with more than CON_FAST contacts */
@@ -482,8 +486,8 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_HEAVY, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= heavy_batches) break;
-        const int idx = b * 32 + lane;
-        const bool have = idx < n_heavy;
+        const int idx = b * P.heavy_lanes + lane;
+        const bool have = lane < P.heavy_lanes && idx < n_heavy;
         int64_t my_env = 0;
         if (have) my_env = (int64_t)P.list[P.e1 - 1 - idx];
         MSOC_TL_BEGIN();
@@ -713,6 +717,10 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     memset(h, 0, sizeof *h);
     h->device = device; h->n = n_envs; h->global_offset = global_env_offset;
     fill_cfg(cfg, h->cfg);
+    if (const char *hl = getenv("MSOC_HEAVY_LANES")) {
+        const int v = atoi(hl);
+        if (v == 8 || v == 16 || v == 32) h->heavy_lanes_override = v;
+    }
     /* every failure below goes through msoc_destroy, which releases whatever exists so far */
     auto bail = [&](int code, const char *what, cudaError_t e) { msoc_destroy(h); return fail(code, what, e); };
 
@@ -825,6 +833,10 @@ static int launch_step(msoc_handle *h, StepParams &P, int64_t e0, int64_t e1, in
 {
     P.e0 = e0; P.e1 = e1; P.chunk = chunk;
     const int64_t m = e1 - e0;
+    /* The heavy kernel is bound by the latency of one warp-batch (the warp walks the union of its lanes' divergent
+       contact work).  With plenty of batches per resident warp full warps give the most throughput; when the heavy envs
+       (~9 % of the range) do not even fill the machine once, batches of fewer envs finish sooner. */
+    P.heavy_lanes = h->heavy_lanes_override ? h->heavy_lanes_override : (m >= HEAVY_FULL_WARP_ENVS ? 32 : 16);
     msoc_step_fast_kernel<<<(unsigned)((m + FAST_BLOCK - 1) / FAST_BLOCK), FAST_BLOCK, FAST_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());

@@ -44,12 +44,12 @@ class Agent(nn.Module):
     def get_action_and_value(self, x, action=None):
         mean = self.actor_mean(x)
         std = torch.exp(self.actor_logstd.expand_as(mean))
-        probs = Normal(mean, std)
+        probs = Normal(mean, std, validate_args=False)  # (validation syncs with the host: not capturable)
         if action is None:
-            action = probs.sample()
+            action = mean + std * torch.randn_like(mean)  # = probs.sample(), without torch.normal's host-side std check
         elif self.rpo_alpha > 0.0:
             z = torch.empty_like(mean).uniform_(-self.rpo_alpha, self.rpo_alpha)
-            probs = Normal(mean + z, std)
+            probs = Normal(mean + z, std, validate_args=False)
         return action, probs.log_prob(action).sum(1), probs.entropy().sum(1), self.critic(x)
 
     def get_deterministic_action(self, x):

@@ -140,27 +140,26 @@ class SoccerEnv(ParallelEnv):
         return observations, rewards, terminations, truncations, infos
 
     def render(self):
-        """Pulls this one env's poses back to the host and draws them with pygame when it is
-        installed (renderer.py); without pygame the call returns the poses and draws nothing."""
+        """Pulls this one env's poses back to the host (msoc_get_state) and draws them with pygame when it is installed
+        (marl_soccer_b200/renderer.py; the reference: soccer_env.py:156-162).  Returns the poses; without pygame nothing
+        is drawn."""
         if self.render_mode != "human":
             return None
         poses = self._game.poses()
-        try:
-            from .renderer import PygameRenderer
-        except Exception:
-            return poses
         if self._renderer is None:
-            self._renderer = PygameRenderer()
-        self._renderer.draw(poses)
+            from .renderer import PygameRenderer
+            try:
+                self._renderer = PygameRenderer()
+            except ImportError:  # pygame is not installed: pose pull-back only
+                self._renderer = False
+        if self._renderer:
+            self._renderer.draw(poses)
         return poses
 
     def close(self):
-        try:
-            if self._renderer is not None:
-                self._renderer.close()
-                self._renderer = None
-        except Exception:
-            pass
+        if self._renderer:
+            self._renderer.close()
+        self._renderer = None
         sim = getattr(self, "_sim", None)
         if sim is not None and hasattr(sim, "close"):
             sim.close()

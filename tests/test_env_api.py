@@ -279,3 +279,28 @@ def test_vec_env_matches_single_envs_on_shared_actions(kind="hostsim"):
             oo, rr, tt, tr, inf = e.step(vec._array_to_dict(a[i]))
             assert np.array_equal(vec._dict_to_array(oo), o[i])
             assert rr["agent_0"] == r[i, 0] and inf["agent_0"]["score"] == infos[i]["agent_0"]["score"]
+
+
+# ------------------------------------------------------------------------------ render pull-back
+def test_render_pulls_back_one_env_and_builds_the_scene():
+    """render() (soccer_env.py:156-162): None unless render_mode == "human"; otherwise the five poses of the env, and
+    the scene primitives flip the y axis like the reference's drawing code (renderer.py:30-42, entities.py:37-57)."""
+    from marl_soccer_b200 import renderer
+    assert make_env().render() is None
+    env = make_env(render_mode="human")
+    env.reset(options={"use_fixed_positions": True})
+    poses = env.render()
+    assert [p for p, _ in poses["agents"]] == [(200.0, 198.0), (200.0, 396.0), (600.0, 198.0), (600.0, 396.0)]
+    assert poses["ball"] == (400.0, 300.0) and abs(poses["agents"][2][1] - math.pi) < 1e-6
+    prims = renderer.scene(poses)
+    polys = [p for p in prims if p[0] == "poly"]
+    assert len(polys) == 8 and polys[0][1] == renderer.BLUE_RGB and polys[4][1] == renderer.RED_RGB
+    # agent_0 at (200, 198), angle 0: the box is 30 x 30 around (200, 600 - 198) on the screen, its nose points to +x
+    xs, ys = [q[0] for q in polys[0][2]], [q[1] for q in polys[0][2]]
+    assert (min(xs), max(xs), min(ys), max(ys)) == (185.0, 215.0, 387.0, 417.0)
+    assert max(q[0] for q in polys[1][2]) == 215.0
+    # agent_2 faces -x (angle pi): its nose tip is on the left edge
+    assert abs(min(q[0] for q in polys[5][2]) - 585.0) < 1e-4
+    ball = prims[-1]
+    assert ball[0] == "circle" and ball[2] == (400.0, 300.0) and ball[3] == 10
+    env.close()
