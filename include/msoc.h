@@ -207,6 +207,12 @@ int msoc_stats_read(msoc_handle *h, msoc_stats *h_out, int reset, void *stream);
 /* Launch accounting for bench.py: number of kernels this library has launched. */
 uint64_t msoc_launch_count(void);
 
+/* Debug aid: bit set of the kernels' own bounds / invariant checks that failed since the last call (list entries
+   inside the stepped range, contact-pool and overflow slots, arbiter-cache counts, env indices of the observation
+   builder, the device-side step counter, non-NaN state).  Only the checked build (libmsoc_checked.so, compiled with
+   -DMSOC_CHECKS by marl_soccer_b200/build.py) evaluates them; the product build returns -1. */
+int msoc_debug_errors(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ EXPORTS = (
     "msoc_last_error", "msoc_version", "msoc_create", "msoc_destroy", "msoc_num_envs", "msoc_reset",
     "msoc_step", "msoc_step_host", "msoc_reset_host", "msoc_read_counters", "msoc_get_state",
     "msoc_set_state", "msoc_get_obs_host", "msoc_step_host_frames", "msoc_stats_device", "msoc_stats_read",
-    "msoc_launch_count", "msoc_device_buffers",
+    "msoc_launch_count", "msoc_device_buffers", "msoc_debug_errors",
 )
 
 
@@ -96,6 +96,7 @@ def declare(L) -> None:
     L.msoc_last_error.restype = C.c_char_p
     L.msoc_version.restype = C.c_int
     L.msoc_launch_count.restype = u64
+    L.msoc_debug_errors.restype = C.c_int
     L.msoc_create.argtypes = [C.POINTER(MsocConfig), i64, C.c_int, u64, u64, C.POINTER(vp)]
     L.msoc_destroy.argtypes = [vp]
     L.msoc_num_envs.argtypes = [vp]

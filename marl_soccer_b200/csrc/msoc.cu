@@ -28,6 +28,10 @@
 
 using namespace msoc;
 
+#ifdef MSOC_CHECKS
+__device__ unsigned int g_msoc_check_bits;
+#endif
+
 /* ------------------------------------------------------------------------------------ errors */
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
@@ -252,6 +256,7 @@ __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, flo
         if (gn < 4) obs_fetch(A, step, mask, gn, my_env, lane, R);
         const int env = __shfl_sync(0xffffffffu, my_env, 8 * g + el);
         if ((m8 >> el) & 1u) {
+            MSOC_CHECK(env >= 0 && env < A.n, CHK_OBS_ENV);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 float o[22];
@@ -423,6 +428,7 @@ __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light
         const int idx = b * 32 + lane;
         const bool have = idx < n_light;
         const int64_t my_env = have ? (int64_t)P.list[P.e0 + idx] : 0;
+        MSOC_CHECK(!have || (my_env >= P.e0 && my_env < P.e1), CHK_LIST_ENV);
         MSOC_TL_BEGIN();
         bool ok = false;
         int load = 0;
@@ -467,6 +473,8 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
     /* this step's fast kernel is complete and the next one starts after this kernel: advance the step counter */
     if (P.chunk < 0 && blockIdx.x == 0 && tid == 0) P.ctl[CTL_STEP_FAST] = (step + 1) % 6;
     const int n_heavy = ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
+    MSOC_CHECK(step >= 0 && step < 6, CHK_STEP_COUNTER);
+    MSOC_CHECK(n_heavy >= 0 && (int64_t)n_heavy + ctl[CTL_LIGHT] <= P.e1 - P.e0, CHK_LIST_COUNT);
     const int heavy_batches = (n_heavy + P.heavy_lanes - 1) / P.heavy_lanes;
 
     Tally T; tally_clear(T);
@@ -490,6 +498,7 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         const bool have = lane < P.heavy_lanes && idx < n_heavy;
         int64_t my_env = 0;
         if (have) my_env = (int64_t)P.list[P.e1 - 1 - idx];
+        MSOC_CHECK(!have || (my_env >= P.e0 && my_env < P.e1), CHK_LIST_ENV);
         MSOC_TL_BEGIN();
         bool ok = false;
         int load = 0;
@@ -675,6 +684,20 @@ extern "C" {
 const char *msoc_last_error(void) { return g_last_error.c_str(); }
 int msoc_version(void) { return MSOC_VERSION; }
 uint64_t msoc_launch_count(void) { return g_launches.load(); }
+/* Bits of the failed kernel checks since the last call (see MSOC_CHECK in step_core.cuh); -1 in a build without
+   -DMSOC_CHECKS.  Synchronises the device. */
+int msoc_debug_errors(void)
+{
+#ifdef MSOC_CHECKS
+    unsigned int bits = 0, zero = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(&bits, g_msoc_check_bits, sizeof bits) != cudaSuccess) return -2;
+    cudaMemcpyToSymbol(g_msoc_check_bits, &zero, sizeof zero);
+    return (int)bits;
+#else
+    return -1;
+#endif
+}
 int64_t msoc_num_envs(const msoc_handle *h) { return h ? h->n : 0; }
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -768,6 +791,8 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
         ce = cudaFuncSetAttribute(msoc_step_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
     if (ce == cudaSuccess)
         ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, LIGHT_BLOCK, LIGHT_SMEM_BYTES);
+    if (const char *cv = getenv("MSOC_FAST_CARVEOUT")) /* experiments: shared-memory carve-out (percent) of the streaming kernel */
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
     if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);

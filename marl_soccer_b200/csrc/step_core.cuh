@@ -37,6 +37,18 @@
 #define MSOC_HD_NOINLINE static
 #endif
 
+/* Debug build only (-DMSOC_CHECKS, marl_soccer_b200/libmsoc_checked.so): bounds and invariant checks of the kernels'
+   indices; a failed check sets a bit in a device word that msoc_debug_errors() returns.  (compute-sanitizer is not
+   available on the GPU pool this was developed on.) */
+#if defined(MSOC_CHECKS) && defined(__CUDA_ARCH__)
+extern __device__ unsigned int g_msoc_check_bits;
+#define MSOC_CHECK(cond, bit) do { if (!(cond)) atomicOr(&g_msoc_check_bits, 1u << (bit)); } while (0)
+#else
+#define MSOC_CHECK(cond, bit) do { } while (0)
+#endif
+enum { CHK_LIST_ENV = 0, CHK_POOL_SLOT = 1, CHK_OVF_SLOT = 2, CHK_CACHE_COUNT = 3, CHK_OBS_ENV = 4, CHK_STEP_COUNTER = 5,
+       CHK_CONTACT_COUNT = 6, CHK_FINITE_STATE = 7, CHK_LIST_COUNT = 8 };
+
 namespace msoc {
 
 /* ------------------------------------------------------------------ constants (game/constants.py) */
@@ -709,6 +721,9 @@ MSOC_HD int contact_alloc(Work &W)
         if (W.n_ovf >= MAXC - CON_FAST) { W.overflow++; return NIL; }
         p = -1 - W.n_ovf++;
     }
+    MSOC_CHECK(p < CON_FS && s_ >= 0, CHK_POOL_SLOT);
+    MSOC_CHECK(p >= -(MAXC - CON_FAST), CHK_OVF_SLOT);
+    MSOC_CHECK(W.nc < MAXC, CHK_CONTACT_COUNT);
     int fs; float *cp = contact_ptr(W, p, fs);
     cp[CF_NEXT * fs] = u2f((uint32_t)NIL);
     if (W.nc == 0) W.head = p;
@@ -1411,6 +1426,8 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #pragma unroll
         for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
+    MSOC_CHECK(new_count >= 0 && new_count <= MAX_CACHE && old_count <= MAX_CACHE, CHK_CACHE_COUNT);
+    MSOC_CHECK(E.px[4] == E.px[4] && E.vx[0] == E.vx[0] && E.ang[3] == E.ang[3], CHK_FINITE_STATE);
     E.flags = (E.flags & ~(FLAG_CACHE_MASK | FLAG_INJECT)) | (uint32_t)new_count;
 
     /* ---- goal test (game/game.py:401-412), strict inequalities */

@@ -52,6 +52,21 @@ class HostBufferSim:
                                            _capi.STEP_AUTO_RESET if auto_reset else 0, None))
         return obs, rew, done, goal
 
+    def step_frames(self, actions, auto_reset: bool = True):
+        """msoc_step_host_frames: like step(), but only the newest 22-float frame of every agent comes back, (N,4,22) --
+        a third of the D2H bytes.  The caller owns the 3-frame stack: append the frame; where `done` is set (and
+        auto_reset) the frame is the first one of the next episode and fills all three slots."""
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 12)
+        frames = np.zeros((self.n, 4, 22), np.float32)
+        rew = np.zeros((self.n, 2), np.float32)
+        done = np.zeros(self.n, np.uint8)
+        goal = np.zeros(self.n, np.int8)
+        self.score = np.zeros((self.n, 2), np.int32)
+        _capi.check(self._L.msoc_step_host_frames(self._h, a.ctypes.data, frames.ctypes.data, rew.ctypes.data,
+                                                  done.ctypes.data, goal.ctypes.data, self.score.ctypes.data,
+                                                  _capi.STEP_AUTO_RESET if auto_reset else 0, None))
+        return frames, rew, done, goal
+
     def get_states(self, idx) -> list:
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         arr = (_capi.MsocEnvState * len(idx))()

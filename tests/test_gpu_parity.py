@@ -144,6 +144,43 @@ def test_global_offset_shards_agree():
             assert np.array_equal(x, np.concatenate([y, z]))
 
 
+def test_chunked_host_step_equals_the_whole_step():
+    """msoc_step_host cuts large batches into pipeline chunks on two streams (H2D and kernels of one chunk overlap the
+    D2H copies of the previous one); msoc_step_host_frames returns only the newest frame.  Both must be the very same
+    simulation as the one-launch device step: bit-identical outputs over steps that include goals and auto-resets."""
+    import torch
+    from marl_soccer_b200 import _capi
+    from marl_soccer_b200.host_api import HostBufferSim
+    from marl_soccer_b200.sim import BatchedSoccerSim
+    n = 200_000  # three chunks
+    cfg = {**P.CONFIG, "simulation": {"max_steps": 9}}
+    host = HostBufferSim(n, cfg, seed=5)
+    fr = HostBufferSim(n, cfg, seed=5)
+    dev = BatchedSoccerSim(n, config=cfg, seed=5)
+    a = host.reset(O.MODE_FULL_RANDOM, seed=2)
+    fr.reset(O.MODE_FULL_RANDOM, seed=2)
+    b = dev.reset(O.MODE_FULL_RANDOM, seed=2)
+    assert np.array_equal(a, b.cpu().numpy())
+    rng = np.random.default_rng(1)
+    stack = a.copy()
+    for t in range(12):
+        act = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)
+        o_h, r_h, d_h, g_h = host.step(act)
+        o_d, r_d, d_d, g_d = dev.step(torch.from_numpy(act).cuda())
+        assert np.array_equal(o_h, o_d.cpu().numpy()) and np.array_equal(r_h, r_d.cpu().numpy()), t
+        assert np.array_equal(d_h, d_d.cpu().numpy()) and np.array_equal(g_h, g_d.cpu().numpy()), t
+        assert np.array_equal(host.score, dev.score.cpu().numpy()), t
+        # frames-only variant: the caller keeps the 3-frame stack (soccer_env.py:130-140, :92-96)
+        frames, r_f, d_f, g_f = fr.step_frames(act)
+        s4 = stack.reshape(n, 4, 3, 22)
+        s4[:, :, 0], s4[:, :, 1], s4[:, :, 2] = s4[:, :, 1].copy(), s4[:, :, 2].copy(), frames
+        fresh = d_f.astype(bool)
+        s4[fresh] = frames[fresh][:, :, None, :]
+        assert np.array_equal(stack, o_h), t
+        assert np.array_equal(r_f, r_h) and np.array_equal(d_f, d_h) and np.array_equal(g_f, g_h)
+    assert d_h.sum() == 0 and host.stats()["episodes"] == n  # everybody truncated once, at step 9
+
+
 def test_ragged_sizes_and_masked_reset():
     """Env counts that are not multiples of the warp/block tile, and masked resets."""
     for n in (1, 31, 33, 127, 129, 1000):
