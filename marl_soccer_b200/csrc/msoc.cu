@@ -320,19 +320,6 @@ constexpr size_t FAST_SMEM_BYTES = (size_t)(FAST_BLOCK / 32) * STAGE_WORDS * siz
 #define MSOC_FAST_MIN_BLOCKS 4
 #endif
 
-/* Appends the envs of the lanes with `want` set at `*tail` (one atomic per warp); slot(i) maps the i-th
-   entry to its address. */
-template <typename SlotFn>
-__device__ __forceinline__ void push_warp(int *tail, bool want, int env, int lane, SlotFn slot)
-{
-    const uint32_t m = __ballot_sync(0xffffffffu, want);
-    if (m == 0u) return;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(tail, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (want) *slot(base + __popc(m & ((1u << lane) - 1u))) = env;
-}
-
 /* warp reduce of the per-rollout statistics (marl-soccer.ipynb:411-429), one atomic per warp and counter */
 __device__ __forceinline__ void flush_tally(const Tally &T, double *stats, int lane)
 {
@@ -385,10 +372,20 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
         ok = step_one_env(MODE_FAST, P, step, my_env, W, load, T);
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
+    /* list slots of the declined envs: the two atomics are in flight while the observations are built */
     const bool declined = have && !ok;
-    push_warp(ctl + CTL_LIGHT, declined && load == 0, (int)my_env, lane, [&](int i) { return P.list + (P.e0 + i); });
-    push_warp(ctl + CTL_HEAVY, declined && load != 0, (int)my_env, lane, [&](int i) { return P.list + (P.e1 - 1 - i); });
+    const uint32_t ml = __ballot_sync(0xffffffffu, declined && load == 0), mh = __ballot_sync(0xffffffffu, declined && load != 0);
+    int base_l = 0, base_h = 0;
+    if (lane == 0) {
+        if (ml != 0u) base_l = atomicAdd(ctl + CTL_LIGHT, __popc(ml));
+        if (mh != 0u) base_h = atomicAdd(ctl + CTL_HEAVY, __popc(mh));
+    }
+    if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
+    base_l = __shfl_sync(0xffffffffu, base_l, 0);
+    base_h = __shfl_sync(0xffffffffu, base_h, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (declined && load == 0) P.list[P.e0 + base_l + __popc(ml & below)] = (int)my_env;
+    if (declined && load != 0) P.list[P.e1 - 1 - (base_h + __popc(mh & below))] = (int)my_env;
     flush_tally(T, P.stats, lane);
     if ((blockIdx.x & 15) == 0 && warp == 0) MSOC_TL_END(0);
 }

@@ -1109,20 +1109,13 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         /* an injected state (Arrays::inject): the general kernel steps it (rare: only the step after msoc_set_state) */
         if (E.flags & FLAG_INJECT) { load = 1; return false; }
     }
-    if (!contact_path && old_count != 0) {
-        /* nothing can touch this step, but the env still carries arbiters of contacts that ended
-           less than collision_persistence (3) steps ago: age them (cpSpaceArbiterSetFilter) */
-        const uint32_t *oc = A.cache[cur] + cache_slot(e, 0);
-        uint32_t *nc_ = A.cache[cur ^ 1] + cache_slot(e, 0);
-        for (int j = 0; j < old_count; j++) {
-            const uint32_t info = oc[3 * j];
-            const uint32_t age = (info >> 10) & 3u;
-            if (age >= 2u) continue;
-            nc_[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
-            nc_[3 * new_count + 1] = oc[3 * j + 1]; nc_[3 * new_count + 2] = oc[3 * j + 2];
-            new_count++;
-        }
-    }
+    const bool age_only = !contact_path && old_count != 0;
+#if defined(__CUDA_ARCH__)
+    /* the env still carries arbiters of contacts that ended less than collision_persistence (3) steps ago; they are aged
+       at the end of the step -- start pulling their cache line now, the shaping and velocity code in between covers the
+       latency */
+    if (age_only) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.cache[cur] + cache_slot(e, 0)));
+#endif
 
     /* ---- shaping rewards (game/game.py:324-349) from the step displacement; only positions enter, so
        they are final here and their inputs need not stay live across the contact path */
@@ -1426,6 +1419,21 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #pragma unroll
         for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
+    if (age_only) {
+        /* nothing can touch this step, but the env still carries arbiters of contacts that ended
+           less than collision_persistence (3) steps ago: age them (cpSpaceArbiterSetFilter) */
+        const uint32_t *oc = A.cache[cur] + cache_slot(e, 0);
+        uint32_t *nc_ = A.cache[cur ^ 1] + cache_slot(e, 0);
+        for (int j = 0; j < old_count; j++) {
+            const uint32_t info = oc[3 * j];
+            const uint32_t age = (info >> 10) & 3u;
+            if (age >= 2u) continue;
+            nc_[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
+            nc_[3 * new_count + 1] = oc[3 * j + 1]; nc_[3 * new_count + 2] = oc[3 * j + 2];
+            new_count++;
+        }
+    }
+
     MSOC_CHECK(new_count >= 0 && new_count <= MAX_CACHE && old_count <= MAX_CACHE, CHK_CACHE_COUNT);
     MSOC_CHECK(E.px[4] == E.px[4] && E.vx[0] == E.vx[0] && E.ang[3] == E.ang[3], CHK_FINITE_STATE);
     E.flags = (E.flags & ~(FLAG_CACHE_MASK | FLAG_INJECT)) | (uint32_t)new_count;
