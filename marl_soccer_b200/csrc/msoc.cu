@@ -2,15 +2,15 @@
  * msoc.cu -- B200 (sm_100a) kernels and the C-ABI (include/msoc.h) of the batched 2v2 soccer
  * simulator.  Replaces the reference's per-env Python/pymunk update loop
  * (soccer_simulation/marl_vecenv.py:30-68 -> soccer_env.py:100-154 -> game/game.py:378-437 ->
- * pymunk Space.step) with one fused device step per vectorised step: three launches, see "The fused step".
+ * pymunk Space.step) with one fused device step per vectorised step: two launches, see "The fused step".
  *
  * Data layout: one 128-byte record per env in each of three rotating buffers (msoc::Arrays in step_core.cuh);
  * one thread owns one env while it is stepped, one warp a batch of 32 envs (consecutive in the streaming kernel,
- * listed in the contact kernels).  The stacked observations (N,4,66) are never read back: once a warp has stored
+ * listed in the contact kernel).  The stacked observations (N,4,66) are never read back: once a warp has stored
  * the new states, the three buffers hold the poses behind the three frames of the stack, and the warp rebuilds
  * the observations of its envs from them -- four lanes per env (one per agent), eight envs at a time, staged in
- * shared memory in the layout of the output and written as whole 1 056-byte blocks with 16-byte stores, so that
- * every DRAM sector is written exactly once and in full.
+ * shared memory in the layout of the output and written as whole 1 056-byte blocks by bulk asynchronous copies, so
+ * that every DRAM sector is written exactly once and in full.
  *
  * There is no CPU fallback in this library: every entry point needs a CUDA device.
  */
@@ -60,8 +60,8 @@ struct DeviceGuard {
 constexpr int MAX_CHUNKS = 8; /* pipeline stages of the host-buffer step */
 /* control block in device memory (ints): two sets of list counters that alternate between steps, the step counters
    that select the ping-pong halves, one set of list counters per pipeline chunk of the host-buffer step */
-enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_HEAVY = 2, CTL_NEXT_LIGHT = 3, CTL_WORDS = 4 };
-enum { CTL_STEP_FAST = 8, CTL_STEP_CONTACT = 9, CTL_CHUNK0 = 16, CTL_TOTAL = CTL_CHUNK0 + CTL_WORDS * MAX_CHUNKS };
+enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_BATCH = 2, CTL_PAIR = 4, CTL_MULTI = 5, CTL_WORDS = 8 };
+enum { CTL_STEP_FAST = 16, CTL_STEP_CONTACT = 17, CTL_CHUNK0 = 24, CTL_TOTAL = CTL_CHUNK0 + CTL_WORDS * MAX_CHUNKS };
 
 struct msoc_handle {
     int device;
@@ -69,7 +69,7 @@ struct msoc_handle {
     uint64_t global_offset;
     SimCfg cfg;
     Arrays A;
-    int sm_count, blocks_per_sm, light_blocks_per_sm; /* persistent grids of the contact and light kernels */
+    int sm_count, blocks_per_sm; /* persistent grid of the contact kernel */
     int heavy_lanes_override; /* MSOC_HEAVY_LANES (experiments): 0 = choose by batch size */
     void *slab;
     /* internal I/O buffers of the host-buffer API */
@@ -79,11 +79,10 @@ struct msoc_handle {
     int32_t *d_score;
     double *d_stats; /* 8 doubles, msoc_stats layout */
     int *d_ctl;      /* CTL_TOTAL ints */
-    int *d_list;     /* n ints: contact list of the step in flight */
+    int *d_list;     /* n ints: contact lists of the step in flight (light from the front of a range, heavy from its back) */
+    int *d_list2;    /* n ints: pair class from the front, multi class from the back */
     float *d_frames; /* (N,4,22) newest frames, msoc_step_host_frames; allocated on first use */
     void *d_inject;  /* Arrays::inject, allocated by the first msoc_set_state */
-    cudaStream_t aux_stream[2];        /* the light kernel runs here, beside the heavy contact kernel */
-    cudaEvent_t ev_listed[2], ev_light[2]; /* fork after the fast kernel / join after the light kernel */
     cudaStream_t pipe_stream;          /* second lane of the chunked host-buffer step */
     cudaEvent_t ev_pipe_fork, ev_pipe_join;
     void *d_stage; size_t stage_bytes; /* get/set_state staging */
@@ -114,6 +113,7 @@ struct StepParams {
     double *stats;        /* 8 */
     int *ctl;             /* the handle's control block */
     int *list;            /* N slots: envs that need the contact path -- light from the front of [e0, e1), heavy from its back */
+    int *list2;           /* N slots: pair class from the front of [e0, e1), multi class from its back */
     int64_t e0, e1;       /* the envs this launch steps */
     uint64_t global_offset;
     uint32_t flags;
@@ -150,7 +150,7 @@ __device__ __forceinline__ int *step_ctl(const StepParams &P, int step) { return
 /* Loads env e (the record of buffer step % 3, or the injected record of a flagged env) and its actions, steps it.  On
    success (always, except for the contact-free mode, which declines envs that need the contact path) the per-env
    outputs and the new state are written; the observation follows in obs_tile once the whole warp has stored. */
-__device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P, int step, int64_t e, Work &W, int &load, Tally &T)
+__device__ __forceinline__ bool step_one_env(const int MODE, const int ALLOWED, const StepParams &P, int step, int64_t e, Work &W, int &load, Tally &T)
 {
     float act[12];
     const float4 *a4 = reinterpret_cast<const float4 *>(P.actions + e * 12);
@@ -165,12 +165,12 @@ __device__ __forceinline__ bool step_one_env(const int MODE, const StepParams &P
     for (int k = 0; k < 12; k++) finite = finite && (fabsf(act[k]) <= 3.0e38f);
     Env E;
     const float4 *rec = P.A.pose[buf_cur(step)] + e * POSE_F4;
-    if (MODE == MODE_FULL) { /* the only kernel that sees injected states */
+    if ((ALLOWED & (1 << MODE_FULL)) && MODE == MODE_FULL) { /* the only kernel that sees injected states */
         if (__float_as_uint(rec[7].z) & FLAG_INJECT) rec = P.A.inject + e * POSE_F4;
     }
     load_env(P.A, rec, e, E);
     StepOut out;
-    if (!env_step(MODE, E, act, P.cfg, P.A, cache_half(step), e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
+    if (!env_step(MODE, ALLOWED, E, act, P.cfg, P.A, cache_half(step), e, P.global_offset + (uint64_t)e, P.flags, W, out, load)) return false;
     reinterpret_cast<float2 *>(P.reward)[e] = make_float2(out.reward, out.reward);
     P.done[e] = out.done;
     P.goal[e] = out.goal;
@@ -288,28 +288,29 @@ __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, flo
     }
 }
 
-/* The fused step is three launches, each tuned for its share of the work.
+/* The fused step is two launches on the caller's stream.
    msoc_step_fast_kernel     streams over ALL envs, thread t of block b steps env e0 + b*128 + t in contact-free
                              mode and its warp writes the observation rows.  No contact code is compiled into
                              it: few registers, small shared memory, small instruction footprint -> many
                              resident warps to hide the HBM latency.  Envs whose broad phase finds a candidate
                              pair (~27 % in the benchmark mix) write nothing and are appended, one atomic per
-                             warp and class, to the step's contact list: light (exactly one agent x wall pair,
-                             the bulk) from the front, heavy (anything else) from the back.
-   msoc_step_light_kernel    every warp of a persistent grid takes batches of 32 light envs, thread per env: one
-                             narrow-phase call and a register-only single-body impulse solver (at most two
-                             contacts); again no solver scratch.
-   msoc_step_contact_kernel  every warp of a persistent grid takes batches of 32 heavy envs and every thread steps
-                             one of them in full mode: narrow phase over all candidate pairs, arbiter cache,
-                             10-iteration impulse solver with bodies and contacts in shared memory; its warp
-                             writes the rows.
-   The divergent, latency-bound contact work therefore always runs on full warps of similar work, and each
-   kind of work gets the register / shared-memory budget (hence the occupancy) that suits it.  The two contact
-   kernels only depend on the fast kernel's lists and are launched on two streams (msoc_step).
+                             warp and class, to the list of their work class (step_core.cuh LOAD_*): light
+                             (exactly one agent x wall pair, the bulk), pair (exactly one agent x agent or
+                             ball x agent pair), multi (only wall candidates, several), heavy (anything else).
+   msoc_step_contact_kernel  every warp of a persistent grid pulls batches of listed envs of ONE class -- heavy
+                             batches first, then multi, pair, light: longest first -- and every thread steps one
+                             env in the mode of its class: the register-only single-body solver (light), islands
+                             of one or two bodies with their contacts in the lane's shared-memory slots (pair,
+                             multi), or the general Chipmunk path (heavy): narrow phase over all candidate pairs,
+                             arbiter cache, 10-iteration impulse solver with bodies and contacts in shared
+                             memory.  The warp then writes the rows.
+   The divergent, latency-bound contact work therefore always runs on warps of similar work, and the few long
+   heavy batches start at once on their own warps while all other warps stream through the rest.  (Separate kernels
+   per class on separate streams were measured to run one after the other, not side by side: profiles/.)
 
    Which half of the ping-pong state is current is a step counter in DEVICE memory (so a captured CUDA graph of any
    number of steps replays correctly): the fast kernel reads ctl[CTL_STEP_FAST] and copies it to ctl[CTL_STEP_CONTACT]
-   for the two contact kernels of the same step; the contact kernel, which only starts when the fast kernel is complete
+   for the contact kernel of the same step; the contact kernel, which only starts when the fast kernel is complete
    and is complete before the next fast kernel starts, writes the incremented counter back. */
 #ifndef MSOC_FAST_BLOCK
 #define MSOC_FAST_BLOCK 128
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
         if (P.chunk < 0 && tid < CTL_WORDS) P.ctl[CTL_WORDS * ((step & 1) ^ 1) + tid] = 0; /* the next step's list counters */
         if (tid == 0) {
             P.ctl[CTL_STEP_CONTACT] = step;
-            atomicAdd(P.stats + 4, (double)(P.e1 - P.e0)); /* every env of the range is stepped by one of the three kernels */
+            atomicAdd(P.stats + 4, (double)(P.e1 - P.e0)); /* every env of the range is stepped by one of the two kernels */
         }
     }
     MSOC_TL_BEGIN();
@@ -363,81 +364,43 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     const bool have = my_env < P.e1;
     Tally T; tally_clear(T);
     Work W; /* never touched in contact-free mode */
-    W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
+    W.ovf = nullptr; W.body = W.pool = W.geom = W.old = W.isl = nullptr; W.pool_count = nullptr;
     bool ok = false;
     int load = 0;
     if (have) {
         /* the oldest of the three records the observation is rebuilt from is not needed by the step: start pulling it */
         asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A.pose[buf_prev(step)] + my_env * POSE_F4));
-        ok = step_one_env(MODE_FAST, P, step, my_env, W, load, T);
+        ok = step_one_env(MODE_FAST, 1 << MODE_FAST, P, step, my_env, W, load, T);
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    /* list slots of the declined envs: the two atomics are in flight while the observations are built */
+    /* list slots of the declined envs, by work class: lanes 0..3 each fetch the base of one class (one atomic per warp and
+       class that occurs); the atomics are in flight while the observations are built */
     const bool declined = have && !ok;
-    const uint32_t ml = __ballot_sync(0xffffffffu, declined && load == 0), mh = __ballot_sync(0xffffffffu, declined && load != 0);
-    int base_l = 0, base_h = 0;
-    if (lane == 0) {
-        if (ml != 0u) base_l = atomicAdd(ctl + CTL_LIGHT, __popc(ml));
-        if (mh != 0u) base_h = atomicAdd(ctl + CTL_HEAVY, __popc(mh));
+    const uint32_t mdec = __ballot_sync(0xffffffffu, declined);
+    uint32_t mclass = 0u; /* the warp's declined lanes of my class */
+    int base = 0;
+    if (mdec != 0u) {
+        const uint32_t b0 = __ballot_sync(0xffffffffu, declined && (load & 1)), b1 = __ballot_sync(0xffffffffu, declined && (load & 2));
+        auto class_mask = [&](int cl) { return mdec & ((cl & 1) ? b0 : ~b0) & ((cl & 2) ? b1 : ~b1); };
+        mclass = class_mask(load);
+        const uint32_t of_lane = class_mask(lane & 3); /* lane c < 4 speaks for class c */
+        if (lane < N_LOADS && of_lane != 0u) {
+            const int word = lane == LOAD_LIGHT ? CTL_LIGHT : lane == LOAD_HEAVY ? CTL_HEAVY : lane == LOAD_PAIR ? CTL_PAIR : CTL_MULTI;
+            base = atomicAdd(ctl + word, __popc(of_lane));
+        }
     }
     if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
-    base_l = __shfl_sync(0xffffffffu, base_l, 0);
-    base_h = __shfl_sync(0xffffffffu, base_h, 0);
-    const uint32_t below = (1u << lane) - 1u;
-    if (declined && load == 0) P.list[P.e0 + base_l + __popc(ml & below)] = (int)my_env;
-    if (declined && load != 0) P.list[P.e1 - 1 - (base_h + __popc(mh & below))] = (int)my_env;
-    flush_tally(T, P.stats, lane);
-    if ((blockIdx.x & 15) == 0 && warp == 0) MSOC_TL_END(0);
-}
-
-/* Light envs (exactly one agent x wall candidate pair, ~82 % of the contact envs): thread t of a batch steps
-   one listed env with the register-only single-body solver of step_core.cuh (MODE_LIGHT).  Like the fast
-   kernel it needs no solver scratch: shared memory only stages the observation blocks. */
-#ifndef MSOC_LIGHT_BLOCK
-#define MSOC_LIGHT_BLOCK 64 /* small blocks: they slip into an SM as soon as one heavy block has left it */
-#endif
-constexpr int LIGHT_BLOCK = MSOC_LIGHT_BLOCK;
-#ifndef MSOC_LIGHT_MIN_BLOCKS
-#define MSOC_LIGHT_MIN_BLOCKS 6 /* register cap 168: no spills; 8 (cap 128) spills and is slower */
-#endif
-constexpr int LIGHT_MIN_BLOCKS = MSOC_LIGHT_MIN_BLOCKS;
-constexpr size_t LIGHT_SMEM_BYTES = (size_t)(LIGHT_BLOCK / 32) * STAGE_WORDS * sizeof(float);
-__global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light_kernel(const __grid_constant__ StepParams P)
-{
-    extern __shared__ __align__(16) float s_dyn[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float *s_warp = s_dyn + warp * STAGE_WORDS;
-    const int step = P.ctl[CTL_STEP_CONTACT];
-    int *ctl = step_ctl(P, step);
-    const int n_light = ctl[CTL_LIGHT]; /* final: the fast kernel has finished */
-    const int batches = (n_light + 31) / 32;
-    Tally T; tally_clear(T);
-    Work W; /* never touched in light mode */
-    W.ovf = nullptr; W.body = W.pool = W.geom = W.old = nullptr; W.pool_count = nullptr;
-#pragma unroll 1
-    while (true) {
-        /* every warp takes its own batches of 32 envs, handed out dynamically: this kernel runs beside the heavy
-           contact kernel and its blocks start whenever an SM has room for them */
-        int b = 0;
-        if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_LIGHT, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= batches) break;
-        const int idx = b * 32 + lane;
-        const bool have = idx < n_light;
-        const int64_t my_env = have ? (int64_t)P.list[P.e0 + idx] : 0;
-        MSOC_CHECK(!have || (my_env >= P.e0 && my_env < P.e1), CHK_LIST_ENV);
-        MSOC_TL_BEGIN();
-        bool ok = false;
-        int load = 0;
-        if (have) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A.pose[buf_prev(step)] + my_env * POSE_F4));
-            ok = step_one_env(MODE_LIGHT, P, step, my_env, W, load, T);
+    if (mdec != 0u) {
+        base = __shfl_sync(0xffffffffu, base, declined ? load : 0);
+        if (declined) {
+            const int rank = base + __popc(mclass & ((1u << lane) - 1u));
+            int *lst = (load == LOAD_LIGHT || load == LOAD_HEAVY) ? P.list : P.list2;
+            const bool front = load == LOAD_LIGHT || load == LOAD_PAIR;
+            lst[front ? P.e0 + rank : P.e1 - 1 - rank] = (int)my_env;
         }
-        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-        if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
-        MSOC_TL_END(1);
     }
     flush_tally(T, P.stats, lane);
+    if ((blockIdx.x & 15) == 0 && warp == 0) MSOC_TL_END(0);
 }
 
 /* Per-warp scratch of 32 x ENV_STRIDE floats: during the contact solve it holds the lanes' solver bodies (30 fields,
@@ -446,12 +409,11 @@ __global__ void __launch_bounds__(LIGHT_BLOCK, LIGHT_MIN_BLOCKS) msoc_step_light
    afterwards the staged observation blocks. */
 static_assert(STAGE_WORDS <= 32 * ENV_STRIDE, "the observation staging must fit the per-warp solver scratch");
 #ifndef MSOC_HEAVY_BLOCK
-#define MSOC_HEAVY_BLOCK 64 /* threads per block of the heavy contact kernel: small, so that an SM's registers and shared
-                               memory are handed to the light kernel block by block as the heavy batches finish */
+#define MSOC_HEAVY_BLOCK 64 /* threads per block of the contact kernel */
 #endif
 constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
 #ifndef MSOC_HEAVY_MIN_BLOCKS
-#define MSOC_HEAVY_MIN_BLOCKS 5 /* register cap 204 */
+#define MSOC_HEAVY_MIN_BLOCKS 4 /* register cap 255: no spills with all four modes compiled in; at 168 registers (5 or 6 blocks) the spills cost more than the extra warps bring */
 #endif
 constexpr int HEAVY_MIN_BLOCKS = MSOC_HEAVY_MIN_BLOCKS;
 
@@ -459,20 +421,29 @@ constexpr int64_t HEAVY_FULL_WARP_ENVS = 393216; /* ranges of at least this many
 constexpr int HEAVY_WARP_WORDS = (32 * ENV_STRIDE + 3) & ~3; /* 16-byte aligned per-warp scratch */
 constexpr size_t STEP_SMEM_BYTES = (size_t)(HEAVY_BLOCK / 32) * HEAVY_WARP_WORDS * sizeof(float);
 
-__global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
+/* All four contact classes in ONE persistent kernel (concurrent kernels with different register / shared-memory shapes
+   were measured to run one after the other on this part, not side by side): every warp pulls batches from one counter
+   over the combined batch space [heavy | multi | pair | light], i.e. longest batches first, so that the few long
+   latency-bound heavy batches start at once on their own warps while all the other warps stream through the rest. */
+template <int MODES>
+__device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_count)
 {
     extern __shared__ __align__(16) float s_dyn[];
-    __shared__ int s_pool_count[HEAVY_BLOCK / 32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * HEAVY_WARP_WORDS;
     const int step = P.ctl[CTL_STEP_CONTACT];
     int *ctl = step_ctl(P, step);
     /* this step's fast kernel is complete and the next one starts after this kernel: advance the step counter */
     if (P.chunk < 0 && blockIdx.x == 0 && tid == 0) P.ctl[CTL_STEP_FAST] = (step + 1) % 6;
-    const int n_heavy = ctl[CTL_HEAVY]; /* final: the fast kernel has finished */
+    /* final: the fast kernel has finished */
+    const int n_heavy = (MODES & (1 << MODE_FULL)) ? ctl[CTL_HEAVY] : 0, n_multi = (MODES & (1 << MODE_MULTI)) ? ctl[CTL_MULTI] : 0;
+    const int n_pair = (MODES & (1 << MODE_PAIR)) ? ctl[CTL_PAIR] : 0, n_light = (MODES & (1 << MODE_LIGHT)) ? ctl[CTL_LIGHT] : 0;
     MSOC_CHECK(step >= 0 && step < 6, CHK_STEP_COUNTER);
-    MSOC_CHECK(n_heavy >= 0 && (int64_t)n_heavy + ctl[CTL_LIGHT] <= P.e1 - P.e0, CHK_LIST_COUNT);
-    const int heavy_batches = (n_heavy + P.heavy_lanes - 1) / P.heavy_lanes;
+    MSOC_CHECK(n_heavy >= 0 && n_light >= 0 && (int64_t)n_heavy + n_light <= P.e1 - P.e0, CHK_LIST_COUNT);
+    MSOC_CHECK(n_multi >= 0 && n_pair >= 0 && (int64_t)n_multi + n_pair <= P.e1 - P.e0, CHK_LIST_COUNT);
+    const int b_heavy = (n_heavy + P.heavy_lanes - 1) / P.heavy_lanes;
+    const int b_multi = b_heavy + (n_multi + 31) / 32, b_pair = b_multi + (n_pair + 31) / 32;
+    const int batches = b_pair + (n_light + 31) / 32;
 
     Tally T; tally_clear(T);
     float ovf_store[MAXC - CON_FAST][CON_FIELDS]; /* local memory, touched only by envs with more than CON_FAST contacts */
@@ -480,21 +451,24 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
     W.ovf = ovf_store;
     W.body = s_warp + lane;
     W.pool = s_warp + BODY_FIELDS * 5 * 32; /* shared by the warp's lanes */
-    W.pool_count = &s_pool_count[warp];
+    W.pool_count = s_pool_count + warp;
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
     W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
+    W.isl = s_warp + BODY_FIELDS * 5 * 32 + lane; /* island modes: their contact slots, in the (then idle) contact pool */
 #pragma unroll 1
     while (true) {
-        /* every WARP takes its own batches of 32 envs, handed out dynamically (the scratch is per warp, so the warps
-           of a block never wait for each other; the batches differ a lot in length) */
         int b = 0;
-        if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_HEAVY, 1);
+        if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_BATCH, 1);
         b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= heavy_batches) break;
-        const int idx = b * P.heavy_lanes + lane;
-        const bool have = lane < P.heavy_lanes && idx < n_heavy;
-        int64_t my_env = 0;
-        if (have) my_env = (int64_t)P.list[P.e1 - 1 - idx];
+        if (b >= batches) break;
+        int mode, idx, count, lanes = 32;
+        const int *slot;
+        if (b < b_heavy)      { mode = MODE_FULL;  lanes = P.heavy_lanes; idx = b * lanes + lane;  count = n_heavy; slot = P.list + (P.e1 - 1 - idx); }
+        else if (b < b_multi) { mode = MODE_MULTI; idx = (b - b_heavy) * 32 + lane; count = n_multi; slot = P.list2 + (P.e1 - 1 - idx); }
+        else if (b < b_pair)  { mode = MODE_PAIR;  idx = (b - b_multi) * 32 + lane; count = n_pair;  slot = P.list2 + (P.e0 + idx); }
+        else                  { mode = MODE_LIGHT; idx = (b - b_pair) * 32 + lane;  count = n_light; slot = P.list + (P.e0 + idx); }
+        const bool have = lane < lanes && idx < count;
+        const int64_t my_env = have ? (int64_t)*slot : 0;
         MSOC_CHECK(!have || (my_env >= P.e0 && my_env < P.e1), CHK_LIST_ENV);
         MSOC_TL_BEGIN();
         bool ok = false;
@@ -503,14 +477,27 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
         __syncwarp();
         if (have) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P.A.pose[buf_prev(step)] + my_env * POSE_F4));
-            ok = step_one_env(MODE_FULL, P, step, my_env, W, load, T);
+            ok = step_one_env(mode, MODES, P, step, my_env, W, load, T);
         }
         const uint32_t mask = __ballot_sync(0xffffffffu, ok);
         /* (obs_tile starts with a __syncwarp: the solver scratch of every lane is dead before it is reused) */
         if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
-        MSOC_TL_END(2);
+        MSOC_TL_END(mode == MODE_FULL ? 2 : mode == MODE_LIGHT ? 1 : 3);
     }
     flush_tally(T, P.stats, lane);
+}
+
+#ifdef MSOC_CONTACT_MAXNREG
+__global__ void __maxnreg__(MSOC_CONTACT_MAXNREG) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
+#else
+__global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
+#endif
+{
+    __shared__ int s_pool_count[HEAVY_BLOCK / 32];
+#ifndef MSOC_CONTACT_MODES
+#define MSOC_CONTACT_MODES ((1 << MODE_FULL) | (1 << MODE_LIGHT) | (1 << MODE_PAIR) | (1 << MODE_MULTI))
+#endif
+    contact_body<MSOC_CONTACT_MODES>(P, s_pool_count);
 }
 
 /* advances the step counter after a chunked host-buffer step (whose contact kernels do not) */
@@ -758,7 +745,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     const size_t o_score = take(n * 2 * sizeof(int32_t));
     const size_t o_stats = take(8 * sizeof(double));
     const size_t o_ctl = take(CTL_TOTAL * sizeof(int));
-    const size_t o_list = take(n * sizeof(int));
+    const size_t o_list = take(n * sizeof(int)), o_list2 = take(n * sizeof(int));
     const size_t total = off;
 
     ce = cudaMalloc(&h->slab, total);
@@ -779,26 +766,17 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     h->d_score = (int32_t *)(base + o_score);
     h->d_stats = (double *)(base + o_stats);
     h->d_ctl = (int *)(base + o_ctl);
-    h->d_list = (int *)(base + o_list);
+    h->d_list = (int *)(base + o_list); h->d_list2 = (int *)(base + o_list2);
 
     ce = cudaFuncSetAttribute(msoc_step_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
-    if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute(msoc_step_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LIGHT_SMEM_BYTES);
-    if (ce == cudaSuccess)
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->light_blocks_per_sm, msoc_step_light_kernel, LIGHT_BLOCK, LIGHT_SMEM_BYTES);
     if (const char *cv = getenv("MSOC_FAST_CARVEOUT")) /* experiments: shared-memory carve-out (percent) of the streaming kernel */
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
     if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);
     if (ce != cudaSuccess || h->blocks_per_sm < 1 || h->sm_count < 1) return bail(MSOC_ERR_CUDA, "msoc_create: occupancy query", ce);
-    for (int k = 0; k < 2 && ce == cudaSuccess; k++) {
-        ce = cudaStreamCreateWithFlags(&h->aux_stream[k], cudaStreamNonBlocking);
-        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_listed[k], cudaEventDisableTiming);
-        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_light[k], cudaEventDisableTiming);
-    }
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->pipe_stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_pipe_fork, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&h->ev_pipe_join, cudaEventDisableTiming);
@@ -822,11 +800,6 @@ int msoc_destroy(msoc_handle *h)
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->d_frames) cudaFree(h->d_frames);
     if (h->d_inject) cudaFree(h->d_inject);
-    for (int k = 0; k < 2; k++) {
-        if (h->ev_listed[k]) cudaEventDestroy(h->ev_listed[k]);
-        if (h->ev_light[k]) cudaEventDestroy(h->ev_light[k]);
-        if (h->aux_stream[k]) cudaStreamDestroy(h->aux_stream[k]);
-    }
     if (h->ev_pipe_fork) cudaEventDestroy(h->ev_pipe_fork);
     if (h->ev_pipe_join) cudaEventDestroy(h->ev_pipe_join);
     if (h->pipe_stream) cudaStreamDestroy(h->pipe_stream);
@@ -849,37 +822,24 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
     return MSOC_OK;
 }
 
-/* the three launches of one step over the envs [e0, e1): `st` carries the fast and the heavy kernel, lane `k` of the
-   handle's auxiliary streams the light kernel */
-static int launch_step(msoc_handle *h, StepParams &P, int64_t e0, int64_t e1, int chunk, int k, cudaStream_t st)
+/* the two launches of one step over the envs [e0, e1), both on `st` */
+static int launch_step(msoc_handle *h, StepParams &P, int64_t e0, int64_t e1, int chunk, cudaStream_t st)
 {
     P.e0 = e0; P.e1 = e1; P.chunk = chunk;
     const int64_t m = e1 - e0;
-    /* The heavy kernel is bound by the latency of one warp-batch (the warp walks the union of its lanes' divergent
-       contact work).  With plenty of batches per resident warp full warps give the most throughput; when the heavy envs
-       (~9 % of the range) do not even fill the machine once, batches of fewer envs finish sooner. */
+    /* A heavy batch is bound by its latency (the warp walks the union of its lanes' divergent contact work).  With
+       plenty of heavy envs full warps give the most throughput; when they (~1.4 % of the range) do not even occupy the
+       resident warps once, batches of fewer envs finish sooner. */
     P.heavy_lanes = h->heavy_lanes_override ? h->heavy_lanes_override : (m >= HEAVY_FULL_WARP_ENVS ? 32 : 16);
     msoc_step_fast_kernel<<<(unsigned)((m + FAST_BLOCK - 1) / FAST_BLOCK), FAST_BLOCK, FAST_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    /* The two contact kernels only depend on the fast kernel's list.  The heavy one (few, long, latency-bound
-       batches: one per warp) goes first and stays on the caller's stream; the light one runs beside it on the
-       handle's own stream and fills the SMs as the heavy blocks drain.  The caller's stream then waits for it. */
+    /* one persistent grid for all contact classes, right behind the streaming kernel */
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
-    const int64_t heavy_blocks_max = (m + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
-    const unsigned grid = (unsigned)(heavy_blocks_max < resident ? heavy_blocks_max : resident);
-    CUDA_TRY(cudaEventRecord(h->ev_listed[k], st));
-    msoc_step_contact_kernel<<<grid, HEAVY_BLOCK, STEP_SMEM_BYTES, st>>>(P);
+    const int64_t blocks_max = (m + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
+    msoc_step_contact_kernel<<<(unsigned)(blocks_max < resident ? blocks_max : resident), HEAVY_BLOCK, STEP_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamWaitEvent(h->aux_stream[k], h->ev_listed[k], 0));
-    const int64_t light_resident = (int64_t)h->sm_count * (h->light_blocks_per_sm > 0 ? h->light_blocks_per_sm : 1);
-    const int64_t light_blocks_max = (m + LIGHT_BLOCK - 1) / LIGHT_BLOCK;
-    msoc_step_light_kernel<<<(unsigned)(light_blocks_max < light_resident ? light_blocks_max : light_resident), LIGHT_BLOCK, LIGHT_SMEM_BYTES, h->aux_stream[k]>>>(P);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(h->ev_light[k], h->aux_stream[k]));
-    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_light[k], 0));
     return MSOC_OK;
 }
 
@@ -889,7 +849,7 @@ static void fill_step_params(msoc_handle *h, StepParams &P, const float *d_actio
     P.A = h->A; P.cfg = h->cfg; P.actions = d_actions; P.obs_out = d_obs_out; P.frames_out = d_frames_out;
     P.reward = d_reward; P.done = d_done; P.goal = d_goal; P.score = d_score; P.stats = h->d_stats;
     P.global_offset = h->global_offset; P.flags = flags;
-    P.ctl = h->d_ctl; P.list = h->d_list;
+    P.ctl = h->d_ctl; P.list = h->d_list; P.list2 = h->d_list2;
 }
 
 int msoc_step(msoc_handle *h, const float *d_actions, float *d_obs_out, float *d_reward,
@@ -900,7 +860,7 @@ int msoc_step(msoc_handle *h, const float *d_actions, float *d_obs_out, float *d
     DeviceGuard guard(h->device);
     StepParams P;
     fill_step_params(h, P, d_actions, d_obs_out, nullptr, d_reward, d_done, d_goal, d_score, flags);
-    return launch_step(h, P, 0, h->n, -1, 0, (cudaStream_t)stream);
+    return launch_step(h, P, 0, h->n, -1, (cudaStream_t)stream);
 }
 
 /* Host-buffer step: the envs are cut into chunks that alternate between two stream lanes, so that the H2D copy and the
@@ -933,7 +893,7 @@ static int step_host_impl(msoc_handle *h, const float *h_actions, float *h_obs, 
     };
     if (chunks == 1) {
         CUDA_TRY(cudaMemcpyAsync(h->d_act, h_actions, (size_t)h->n * 12 * sizeof(float), cudaMemcpyHostToDevice, st));
-        int rc = launch_step(h, P, 0, h->n, -1, 0, st);
+        int rc = launch_step(h, P, 0, h->n, -1, st);
         if (rc != MSOC_OK) return rc;
         rc = copies_back(0, h->n, st);
         if (rc != MSOC_OK) return rc;
@@ -948,7 +908,7 @@ static int step_host_impl(msoc_handle *h, const float *h_actions, float *h_obs, 
         if (e0 >= e1) break;
         cudaStream_t s = (c & 1) ? h->pipe_stream : st;
         CUDA_TRY(cudaMemcpyAsync(h->d_act + e0 * 12, h_actions + e0 * 12, (size_t)(e1 - e0) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-        int rc = launch_step(h, P, e0, e1, c, c & 1, s);
+        int rc = launch_step(h, P, e0, e1, c, s);
         if (rc != MSOC_OK) return rc;
         rc = copies_back(e0, e1 - e0, s);
         if (rc != MSOC_OK) return rc;

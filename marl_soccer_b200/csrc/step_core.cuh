@@ -692,6 +692,7 @@ struct Work {
                     (an env takes as many as it has contacts; on the average that is far fewer than CON_FAST per lane) */
     int *pool_count; /* slots handed out so far (shared by the warp) */
     float *geom; /* word g: geom[g*SCR] */
+    float *isl;  /* island modes: contact slot k, field f: isl[(k*ISL_FIELDS + f)*SCR] (in the kernel: the idle contact pool) */
     float *old;  /* preloaded cache entry j < OLD_FAST: info old[j*SCR] (bits), jn old[(OLD_FAST+j)*SCR], jt old[(2*OLD_FAST+j)*SCR] */
     float (*ovf)[CON_FIELDS]; /* only when the pool is exhausted (rare): caller-provided array of MAXC - CON_FAST records, field
                                  stride 1 (a pointer, so that the scalar members of this struct stay in registers) */
@@ -974,19 +975,37 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
    still carries cached arbiters; such envs are then stepped in full mode (FAST = false, always returns
    true) on a compacted set of threads.  (A runtime flag, not a template: one copy of the code.)  `load` is the work class of a
    declined env (0 light, 1 heavy; see below), used to batch envs of similar contact work.  W is only touched when !FAST. */
-enum { MODE_FULL = 0, MODE_FAST = 1, MODE_LIGHT = 2 };
+enum { MODE_FULL = 0, MODE_FAST = 1, MODE_LIGHT = 2, MODE_PAIR = 3, MODE_MULTI = 4 };
+/* work classes of the envs the contact-free mode declines (`load`): each has its own list and its own code path */
+enum { LOAD_LIGHT = 0, /* exactly one candidate pair, agent x segment: MODE_LIGHT */
+       LOAD_HEAVY = 1, /* anything else: the general Chipmunk path, MODE_FULL */
+       LOAD_PAIR = 2,  /* exactly one candidate pair, agent x agent or ball x agent: MODE_PAIR */
+       LOAD_MULTI = 3, /* only static candidates (agent x segment, ball x wall), at most two per body: MODE_MULTI */
+       N_LOADS = 4 };
+MSOC_HD int mode_of_load(int load) { return load == LOAD_LIGHT ? MODE_LIGHT : load == LOAD_PAIR ? MODE_PAIR : load == LOAD_MULTI ? MODE_MULTI : MODE_FULL; }
 MSOC_HD float sel4(const float *a, int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
-MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e,
+/* Contacts of a register-resident island (MODE_PAIR, MODE_MULTI): the solver fields of a pool record.  The islands of
+   these modes share no dynamic body with anything else, so solving them on their own, contacts in arbiter order, is the
+   same arithmetic as the general path's sweep over all contacts of the env. */
+enum { IF_NX, IF_NY, IF_RN1, IF_RT1, IF_RN2, IF_RT2, IF_NM, IF_TM, IF_BIAS, IF_BNC, IF_JN, IF_JT, IF_JB, IF_INFO, ISL_FIELDS };
+enum { IF_U = IF_RN1 }; /* a static x body contact has no first arm: its slot carries the friction coefficient there */
+constexpr int ISL_SLOTS = 4;
+
+MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *act, const SimCfg &c, const Arrays &A, int cur, int64_t e,
                       uint64_t gidx, uint32_t step_flags, Work &W, StepOut &out, int &load)
 {
-    const bool FAST = MODE == MODE_FAST, LIGHT = MODE == MODE_LIGHT;
-    /* light mode: the first four cached arbiter entries (one or two sectors) are fetched right away, so that their
-       latency is covered by the prologue */
+    /* ALLOWED: bit m set = the caller may pass MODE == m (a compile-time constant at every call site, so that a kernel
+       only carries the code of its own modes even where MODE itself is a run-time value) */
+    const bool FAST = (ALLOWED & (1 << MODE_FAST)) && MODE == MODE_FAST, LIGHT = (ALLOWED & (1 << MODE_LIGHT)) && MODE == MODE_LIGHT;
+    const bool PAIR = (ALLOWED & (1 << MODE_PAIR)) && MODE == MODE_PAIR, MULTI = (ALLOWED & (1 << MODE_MULTI)) && MODE == MODE_MULTI;
+    const bool FULL = (ALLOWED & (1 << MODE_FULL)) && MODE == MODE_FULL;
+    /* register-only modes: the first four cached arbiter entries (one or two sectors) are fetched right away, so that
+       their latency is covered by the prologue */
     uint32_t pc[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) pc[k] = 0u;
-    if (LIGHT && (E.flags & FLAG_CACHE_MASK) != 0u) {
+    if ((LIGHT || PAIR || MULTI) && (E.flags & FLAG_CACHE_MASK) != 0u) {
 #if defined(__CUDA_ARCH__)
         const uint4 *q = reinterpret_cast<const uint4 *>(A.cache[cur] + cache_slot(e, 0));
         const uint4 q0 = q[0], q1 = q[1], q2 = q[2];
@@ -1096,18 +1115,29 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
 #else
     const bool contact_path = any_candidate || old_count != 0;
 #endif
-    load = 0;
-    const bool run_contacts = MODE == MODE_FULL && contact_path;
+    load = LOAD_LIGHT;
+    const bool run_contacts = FULL && contact_path;
     const bool run_light = LIGHT && contact_path;
+    const bool run_pair = PAIR && contact_path, run_multi = MULTI && contact_path;
     if (FAST) {
         if (contact_path) {
-            /* work class for the contact queues: 0 = exactly one candidate pair and it is agent x segment
-               (the bulk: an agent touching a wall), 1 = anything else (several pairs, agent x agent, ball) */
-            load = (popc32(m_as) == 1 && (m_aa | m_ba | m_bw) == 0u && !(E.flags & FLAG_INJECT)) ? 0 : 1;
+            /* work class for the contact lists */
+            const uint32_t dyn = m_aa | (m_ba << 6);
+            const int n_as = popc32(m_as), n_dyn = popc32(dyn), n_bw = popc32(m_bw);
+            if (E.flags & FLAG_INJECT) load = LOAD_HEAVY;
+            else if (n_dyn == 0) {
+                if (n_as == 1 && n_bw == 0) load = LOAD_LIGHT;
+                else {
+                    bool ok = n_bw <= 2;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) ok = ok && popc32((m_as >> (8 * i)) & 255u) <= 2;
+                    load = ok ? LOAD_MULTI : LOAD_HEAVY;
+                }
+            } else load = (n_dyn == 1 && n_as == 0 && n_bw == 0) ? LOAD_PAIR : LOAD_HEAVY;
             return false;
         }
         /* an injected state (Arrays::inject): the general kernel steps it (rare: only the step after msoc_set_state) */
-        if (E.flags & FLAG_INJECT) { load = 1; return false; }
+        if (E.flags & FLAG_INJECT) { load = LOAD_HEAVY; return false; }
     }
     const bool age_only = !contact_path && old_count != 0;
 #if defined(__CUDA_ARCH__)
@@ -1153,14 +1183,17 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         }
     }
 
-    if (run_contacts) {
+    const bool run_islands = run_pair || run_multi;
+    if (run_contacts || run_islands) {
         /* park what the contact path needs with a dynamic body index (and what it does not need at
            all until it is over) in the lane's scratch: pre-update velocities for the arbiter
            pre-step, poses for the narrow phase */
 #pragma unroll
         for (int i = 0; i < 5; i++) {
+            /* (island modes keep the pre-update velocities in the bias fields until the body's island is solved) */
             float *pb = W.body + i * SCR;
-            pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
+            pb[(run_islands ? BF_BX : BF_VX) * BODY_FS] = E.vx[i]; pb[(run_islands ? BF_BY : BF_VY) * BODY_FS] = E.vy[i];
+            pb[(run_islands ? BF_BW : BF_W) * BODY_FS] = E.w[i];
             W.geom[(GF_PX + i) * SCR] = E.px[i]; W.geom[(GF_PY + i) * SCR] = E.py[i];
         }
 #pragma unroll
@@ -1188,6 +1221,14 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         const float l2 = vx * vx + vy * vy;
         if (l2 > c.max_velocity * c.max_velocity) { const float s_ = c.max_velocity * rsqrt_f(l2); vx *= s_; vy *= s_; }
         E.vx[i] = vx; E.vy[i] = vy;
+    }
+    if (run_islands) {
+        /* the islands fetch and return their bodies by (dynamic) index */
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            float *pb = W.body + i * SCR;
+            pb[BF_VX * BODY_FS] = E.vx[i]; pb[BF_VY * BODY_FS] = E.vy[i]; pb[BF_W * BODY_FS] = E.w[i];
+        }
     }
 
     if (run_light) {
@@ -1296,6 +1337,272 @@ MSOC_HD bool env_step(const int MODE, Env &E, const float *act, const SimCfg &c,
         for (int j = 0; j < 4; j++)
             if (j < old_count) age_entry(pc[3 * j], pc[3 * j + 1], pc[3 * j + 2]);
         for (int j = 4; j < old_count; j++) age_entry(oc[3 * j], oc[3 * j + 1], oc[3 * j + 2]);
+    }
+
+    else if (run_islands) {
+        /* ---- islands of one or two dynamic bodies: the bodies in registers, their contacts in the lane's slots.  Cached
+           arbiter entries: the first four are in pc[], the rest in global memory. */
+        const uint32_t *oc = A.cache[cur] + cache_slot(e, 0);
+        uint32_t *nc_ = A.cache[cur ^ 1] + cache_slot(e, 0);
+        uint64_t touched = 0ull;
+        uint32_t solved = 0u; /* bodies whose bias fields hold bias velocities (not the parked pre-update velocities any more) */
+        const float *G = W.geom;
+        /* cpArbiterUpdate for the arbiter `pair` with the manifold keys k0, k1 (k1 < 0: one contact): accumulated
+           impulses of equal-key contacts, first-contact state */
+        bool first; float cjn0, cjt0, cjn1, cjt1;
+        auto cache_lookup = [&](int pair, int k0, int k1) {
+            first = true; cjn0 = cjt0 = cjn1 = cjt1 = 0.0f;
+            auto one = [&](uint32_t info, uint32_t wjn, uint32_t wjt) {
+                if ((int)(info & 63u) != pair) return;
+                if (((info >> 10) & 3u) == 0u) first = false;
+                const int key = (int)((info >> 6) & 15u);
+                if (key == k0) { cjn0 = u2f(wjn); cjt0 = u2f(wjt); }
+                if (k1 >= 0 && key == k1) { cjn1 = u2f(wjn); cjt1 = u2f(wjt); }
+            };
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < old_count) one(pc[3 * j], pc[3 * j + 1], pc[3 * j + 2]);
+            for (int j = 4; j < old_count; j++) one(oc[3 * j], oc[3 * j + 1], oc[3 * j + 2]);
+        };
+
+        if (run_pair) {
+            /* ---- exactly one candidate pair and it joins two dynamic bodies: agent i x agent j (a = i, b = j) or
+               ball x agent (a = ball, b = agent); at most two contacts */
+            const bool aa = m_aa != 0u;
+            const int idx = aa ? ctz32(m_aa) : ctz32(m_ba);
+            const int ia_ = aa ? ((idx < 3) ? 0 : (idx < 5) ? 1 : 2) : BALL;
+            const int ib_ = aa ? ((idx < 3) ? idx + 1 : (idx < 5) ? idx - 1 : 3) : idx;
+            const int pair = (aa ? PAIR_AGENT_AGENT : PAIR_BALL_AGENT) + idx;
+            float *pa = W.body + ia_ * SCR, *pb = W.body + ib_ * SCR;
+            const V2 off = mk(G[(GF_PX + ib_) * SCR] - G[(GF_PX + ia_) * SCR], G[(GF_PY + ib_) * SCR] - G[(GF_PY + ia_) * SCR]); /* centre b - centre a */
+            Manifold m;
+            V2 r1_off = mk(0.0f, 0.0f), r2_off = mk(0.0f, 0.0f);
+            if (aa) { collide_box_box(G[(GF_CS + (ia_ & 3)) * SCR], G[(GF_SN + (ia_ & 3)) * SCR], G[(GF_CS + ib_) * SCR], G[(GF_SN + ib_) * SCR], off, m); r2_off = off; }
+            else { const V2 cb = vneg(off); collide_ball_box(cb, G[(GF_CS + ib_) * SCR], G[(GF_SN + ib_) * SCR], m); r1_off = cb; }
+            n_contacts = m.count;
+            if (m.count > 0) {
+                const bool two = m.count > 1;
+                touched |= 1ull << pair;
+                solved |= (1u << ia_) | (1u << ib_);
+                cache_lookup(pair, m.key[0], two ? m.key[1] : -1);
+                const float ma = aa ? c.agent_minv : c.ball_minv, iam = aa ? c.agent_iinv : c.ball_iinv;
+                const float mb = c.agent_minv, ibm = c.agent_iinv;
+                const float e_ = aa ? E_AGENT_AGENT : E_BALL_AGENT, u = aa ? U_AGENT_AGENT : U_BALL_AGENT;
+                const float nx = m.n.x, ny = m.n.y;
+                const V2 tng = vperp(m.n);
+                /* pre-update velocities: parked in the bias fields */
+                const float oax = pa[BF_BX * BODY_FS], oay = pa[BF_BY * BODY_FS], oaw = pa[BF_BW * BODY_FS];
+                const float obx = pb[BF_BX * BODY_FS], oby = pb[BF_BY * BODY_FS], obw = pb[BF_BW * BODY_FS];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (i == 0 || two) {
+                        float *q = W.isl + i * ISL_FIELDS * SCR;
+                        const V2 r1 = m.p1[i] - r1_off, r2 = m.p2[i] - r2_off;
+                        const float rn1 = vcross(r1, m.n), rt1 = vcross(r1, tng), rn2 = vcross(r2, m.n), rt2 = vcross(r2, tng);
+                        q[IF_RN1 * SCR] = rn1; q[IF_RT1 * SCR] = rt1; q[IF_RN2 * SCR] = rn2; q[IF_RT2 * SCR] = rt2;
+                        q[IF_NM * SCR] = 1.0f / (ma + iam * rn1 * rn1 + mb + ibm * rn2 * rn2);
+                        q[IF_TM * SCR] = 1.0f / (ma + iam * rt1 * rt1 + mb + ibm * rt2 * rt2);
+                        q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[i] - m.p1[i], m.n) + SLOP);
+                        float vn = 0.0f;
+                        vn -= oax * nx + oay * ny + oaw * rn1;
+                        vn += obx * nx + oby * ny + obw * rn2;
+                        q[IF_BNC * SCR] = vn * e_;
+                        q[IF_JN * SCR] = (i == 0) ? cjn0 : cjn1; q[IF_JT * SCR] = (i == 0) ? cjt0 : cjt1; q[IF_JB * SCR] = 0.0f;
+                    }
+                }
+                float avx = pa[BF_VX * BODY_FS], avy = pa[BF_VY * BODY_FS], aw = pa[BF_W * BODY_FS], abx = 0.0f, aby = 0.0f, abw = 0.0f;
+                float bvx = pb[BF_VX * BODY_FS], bvy = pb[BF_VY * BODY_FS], bw_ = pb[BF_W * BODY_FS], bbx = 0.0f, bby = 0.0f, bbw = 0.0f;
+                /* cpArbiterApplyCachedImpulse (skipped in an arbiter's first step) */
+                if (!first) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (i == 0 || two) {
+                            const float *q = W.isl + i * ISL_FIELDS * SCR;
+                            const float jn = q[IF_JN * SCR], jt = q[IF_JT * SCR];
+                            const float jx = nx * jn - ny * jt, jy = ny * jn + nx * jt;
+                            avx -= jx * ma; avy -= jy * ma; aw -= iam * (q[IF_RN1 * SCR] * jn + q[IF_RT1 * SCR] * jt);
+                            bvx += jx * mb; bvy += jy * mb; bw_ += ibm * (q[IF_RN2 * SCR] * jn + q[IF_RT2 * SCR] * jt);
+                        }
+                    }
+                }
+                /* cpArbiterApplyImpulse x 10 */
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+                for (int it = 0; it < SOLVER_ITERS; it++) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (i == 0 || two) {
+                            float *q = W.isl + i * ISL_FIELDS * SCR;
+                            const float rn1 = q[IF_RN1 * SCR], rt1 = q[IF_RT1 * SCR], rn2 = q[IF_RN2 * SCR], rt2 = q[IF_RT2 * SCR];
+                            const float nM = q[IF_NM * SCR], jbO = q[IF_JB * SCR], jnO = q[IF_JN * SCR], jtO = q[IF_JT * SCR];
+                            float vrn = bvx * nx + bvy * ny + bw_ * rn2;
+                            float vrt = bvy * nx - bvx * ny + bw_ * rt2;
+                            float vbn = bbx * nx + bby * ny + bbw * rn2;
+                            vrn -= avx * nx + avy * ny + aw * rn1;
+                            vrt -= avy * nx - avx * ny + aw * rt1;
+                            vbn -= abx * nx + aby * ny + abw * rn1;
+                            const float jbN = fmaxf(jbO + (q[IF_BIAS * SCR] - vbn) * nM, 0.0f);
+                            const float jnN = fmaxf(jnO - (q[IF_BNC * SCR] + vrn) * nM, 0.0f);
+                            const float jtMax = u * jnN;
+                            const float jtN = fminf(fmaxf(jtO - vrt * q[IF_TM * SCR], -jtMax), jtMax);
+                            const float djb = jbN - jbO, djn = jnN - jnO, djt = jtN - jtO;
+                            q[IF_JB * SCR] = jbN; q[IF_JN * SCR] = jnN; q[IF_JT * SCR] = jtN;
+                            const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+                            bbx += nx * djb * mb; bby += ny * djb * mb; bbw += ibm * rn2 * djb;
+                            bvx += jx * mb; bvy += jy * mb; bw_ += ibm * (rn2 * djn + rt2 * djt);
+                            abx -= nx * djb * ma; aby -= ny * djb * ma; abw -= iam * rn1 * djb;
+                            avx -= jx * ma; avy -= jy * ma; aw -= iam * (rn1 * djn + rt1 * djt);
+                        }
+                    }
+                }
+                pa[BF_VX * BODY_FS] = avx; pa[BF_VY * BODY_FS] = avy; pa[BF_W * BODY_FS] = aw;
+                pa[BF_BX * BODY_FS] = abx; pa[BF_BY * BODY_FS] = aby; pa[BF_BW * BODY_FS] = abw;
+                pb[BF_VX * BODY_FS] = bvx; pb[BF_VY * BODY_FS] = bvy; pb[BF_W * BODY_FS] = bw_;
+                pb[BF_BX * BODY_FS] = bbx; pb[BF_BY * BODY_FS] = bby; pb[BF_BW * BODY_FS] = bbw;
+                /* this step's contacts open the arbiter cache of the next step (age 0) */
+                nc_[0] = (uint32_t)pair | ((uint32_t)m.key[0] << 6); nc_[1] = f2u(W.isl[IF_JN * SCR]); nc_[2] = f2u(W.isl[IF_JT * SCR]);
+                new_count = 1;
+                if (two) {
+                    const float *q = W.isl + ISL_FIELDS * SCR;
+                    nc_[3] = (uint32_t)pair | ((uint32_t)m.key[1] << 6); nc_[4] = f2u(q[IF_JN * SCR]); nc_[5] = f2u(q[IF_JT * SCR]);
+                    new_count = 2;
+                }
+            }
+        }
+
+        if (run_multi) {
+            /* ---- only static candidates: every touched body is an island of its own -- one dynamic body against the
+               static one, at most two arbiters (four contacts) -- solved one after the other, bodies and arbiters in
+               ascending order (the canonical arbiter order restricted to this env) */
+            uint32_t bodies = ((m_as & 0xffu) ? 1u : 0u) | ((m_as & 0xff00u) ? 2u : 0u) | ((m_as & 0xff0000u) ? 4u : 0u) |
+                              ((m_as & 0xff000000u) ? 8u : 0u) | (m_bw ? 16u : 0u);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            while (bodies) {
+                const int b = ctz32(bodies);
+                bodies &= bodies - 1u;
+                const bool ag = b < 4;
+                uint32_t segs = ag ? ((m_as >> (8 * b)) & 255u) : m_bw;
+                float *pb = W.body + b * SCR;
+                const V2 pos = mk(G[(GF_PX + b) * SCR], G[(GF_PY + b) * SCR]);
+                const float bcs = G[(GF_CS + (b & 3)) * SCR], bsn = G[(GF_SN + (b & 3)) * SCR];
+                const float obx = pb[BF_BX * BODY_FS], oby = pb[BF_BY * BODY_FS], obw = pb[BF_BW * BODY_FS]; /* pre-update velocity */
+                const float mb = ag ? c.agent_minv : c.ball_minv, ibm = ag ? c.agent_iinv : c.ball_iinv;
+                const float e_ = ag ? E_AGENT_SEG : E_BALL_WALL;
+                uint32_t firsts = 0u;
+                int cnt = 0;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+                while (segs) {
+                    const int sg = ctz32(segs);
+                    segs &= segs - 1u;
+                    const Seg g = get_segment(sg);
+                    Manifold m;
+                    if (ag) collide_segment_box(g, pos, bcs, bsn, m);
+                    else collide_ball_segment(g, pos, m);
+                    if (m.count == 0) continue;
+                    const int pair = ag ? 8 * b + sg : PAIR_BALL_WALL + sg;
+                    const bool two = m.count > 1;
+                    touched |= 1ull << pair;
+                    cache_lookup(pair, m.key[0], two ? m.key[1] : -1);
+                    /* stored with the dynamic body second (add_contacts): a ball x wall manifold (ball first) is flipped */
+                    const V2 n_ = ag ? m.n : vneg(m.n), tng = vperp(n_);
+                    const float u_ = ag ? ((sg < 6) ? U_AGENT_WALL : U_AGENT_GOALLINE) : U_BALL_WALL;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if ((i == 0 || two) && cnt < ISL_SLOTS) {
+                            float *q = W.isl + cnt * ISL_FIELDS * SCR;
+                            const V2 r2 = ag ? m.p2[i] : m.p1[i];
+                            const float rn = vcross(r2, n_), rt = vcross(r2, tng);
+                            q[IF_NX * SCR] = n_.x; q[IF_NY * SCR] = n_.y; q[IF_RN2 * SCR] = rn; q[IF_RT2 * SCR] = rt;
+                            q[IF_NM * SCR] = 1.0f / (mb + ibm * rn * rn); q[IF_TM * SCR] = 1.0f / (mb + ibm * rt * rt);
+                            q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[i] - m.p1[i], m.n) + SLOP);
+                            q[IF_BNC * SCR] = (obx * n_.x + oby * n_.y + obw * rn) * e_;
+                            q[IF_JN * SCR] = (i == 0) ? cjn0 : cjn1; q[IF_JT * SCR] = (i == 0) ? cjt0 : cjt1; q[IF_JB * SCR] = 0.0f;
+                            q[IF_U * SCR] = u_;
+                            q[IF_INFO * SCR] = u2f((uint32_t)pair | ((uint32_t)m.key[i] << 6));
+                            if (first) firsts |= 1u << cnt;
+                            cnt++;
+                        }
+                    }
+                }
+                solved |= 1u << b;
+                float vx = pb[BF_VX * BODY_FS], vy = pb[BF_VY * BODY_FS], w = pb[BF_W * BODY_FS], bx = 0.0f, by = 0.0f, bw = 0.0f;
+                /* cpArbiterApplyCachedImpulse (skipped for arbiters in their first step) */
+                for (int k = 0; k < cnt; k++) {
+                    if (!((firsts >> k) & 1u)) {
+                        const float *q = W.isl + k * ISL_FIELDS * SCR;
+                        const float nx = q[IF_NX * SCR], ny = q[IF_NY * SCR], jn = q[IF_JN * SCR], jt = q[IF_JT * SCR];
+                        const float jx = nx * jn - ny * jt, jy = ny * jn + nx * jt;
+                        vx += jx * mb; vy += jy * mb; w += ibm * (q[IF_RN2 * SCR] * jn + q[IF_RT2 * SCR] * jt);
+                    }
+                }
+                /* cpArbiterApplyImpulse x 10 */
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+                for (int it = 0; it < SOLVER_ITERS; it++) {
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+                    for (int k = 0; k < cnt; k++) {
+                        float *q = W.isl + k * ISL_FIELDS * SCR;
+                        const float nx = q[IF_NX * SCR], ny = q[IF_NY * SCR], rn = q[IF_RN2 * SCR], rt = q[IF_RT2 * SCR];
+                        const float nM = q[IF_NM * SCR], jbO = q[IF_JB * SCR], jnO = q[IF_JN * SCR], jtO = q[IF_JT * SCR];
+                        const float vrn = vx * nx + vy * ny + w * rn;
+                        const float vrt = vy * nx - vx * ny + w * rt;
+                        const float vbn = bx * nx + by * ny + bw * rn;
+                        const float jbN = fmaxf(jbO + (q[IF_BIAS * SCR] - vbn) * nM, 0.0f);
+                        const float jnN = fmaxf(jnO - (q[IF_BNC * SCR] + vrn) * nM, 0.0f);
+                        const float jtMax = q[IF_U * SCR] * jnN;
+                        const float jtN = fminf(fmaxf(jtO - vrt * q[IF_TM * SCR], -jtMax), jtMax);
+                        const float djb = jbN - jbO, djn = jnN - jnO, djt = jtN - jtO;
+                        q[IF_JB * SCR] = jbN; q[IF_JN * SCR] = jnN; q[IF_JT * SCR] = jtN;
+                        const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+                        bx += nx * djb * mb; by += ny * djb * mb; bw += ibm * rn * djb;
+                        vx += jx * mb; vy += jy * mb; w += ibm * (rn * djn + rt * djt);
+                    }
+                }
+                pb[BF_VX * BODY_FS] = vx; pb[BF_VY * BODY_FS] = vy; pb[BF_W * BODY_FS] = w;
+                pb[BF_BX * BODY_FS] = bx; pb[BF_BY * BODY_FS] = by; pb[BF_BW * BODY_FS] = bw;
+                /* this step's contacts open the arbiter cache of the next step (age 0) */
+                for (int k = 0; k < cnt; k++) {
+                    const float *q = W.isl + k * ISL_FIELDS * SCR;
+                    nc_[3 * new_count] = f2u(q[IF_INFO * SCR]); nc_[3 * new_count + 1] = f2u(q[IF_JN * SCR]); nc_[3 * new_count + 2] = f2u(q[IF_JT * SCR]);
+                    new_count++;
+                }
+                n_contacts += cnt;
+            }
+        }
+
+        /* then the untouched arbiters younger than collision_persistence (3) */
+        auto age_entry = [&](uint32_t info, uint32_t wjn, uint32_t wjt) {
+            const uint32_t age = (info >> 10) & 3u;
+            if (((touched >> (info & 63u)) & 1ull) || age >= 2u) return;
+            if (new_count >= MAX_CACHE) { overflow++; return; }
+            nc_[3 * new_count] = (info & 1023u) | ((age + 1u) << 10);
+            nc_[3 * new_count + 1] = wjn; nc_[3 * new_count + 2] = wjt;
+            new_count++;
+        };
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (j < old_count) age_entry(pc[3 * j], pc[3 * j + 1], pc[3 * j + 2]);
+        for (int j = 4; j < old_count; j++) age_entry(oc[3 * j], oc[3 * j + 1], oc[3 * j + 2]);
+        /* the env back from the scratch (bias fields of unsolved bodies still hold the parked pre-update velocities) */
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const float *pb = W.body + i * SCR;
+            const bool sv = (solved >> i) & 1u;
+            E.vx[i] = pb[BF_VX * BODY_FS]; E.vy[i] = pb[BF_VY * BODY_FS]; E.w[i] = pb[BF_W * BODY_FS];
+            E.vbx[i] = sv ? pb[BF_BX * BODY_FS] : 0.0f; E.vby[i] = sv ? pb[BF_BY * BODY_FS] : 0.0f;
+            if (i < 4) E.wb[i] = sv ? pb[BF_BW * BODY_FS] : 0.0f;
+            E.px[i] = W.geom[(GF_PX + i) * SCR]; E.py[i] = W.geom[(GF_PY + i) * SCR];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) E.ang[i] = W.geom[(GF_ANG + i) * SCR];
     }
 
     if (run_contacts) {

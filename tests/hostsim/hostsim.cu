@@ -119,19 +119,20 @@ void hsim_step(HostSim *h, const float *actions, float *obs_out, float *reward, 
         StepOut out;
         /* same flow as the kernels: contact-free fast pass first, the light or the general pass if it declines */
         int load = 0;
-        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST], geom[GEOM_WORDS], oldc[3 * OLD_FAST];
+        float body[BODY_FIELDS * 5], con[CON_FIELDS * CON_FAST], geom[GEOM_WORDS], oldc[3 * OLD_FAST], isl[ISL_FIELDS * ISL_SLOTS];
         float ovf_store[MAXC - CON_FAST][CON_FIELDS];
         Work W;
         W.ovf = ovf_store;
         int pool_count = 0;
-        W.body = body; W.pool = con; W.pool_count = &pool_count; W.geom = geom; W.old = oldc;
+        W.body = body; W.pool = con; W.pool_count = &pool_count; W.geom = geom; W.old = oldc; W.isl = isl;
         const uint64_t gidx = h->global_offset + (uint64_t)e;
-        if (!env_step(MODE_FAST, E, actions + e * 12, h->cfg, h->A, cache_half(step), e, gidx, flags, W, out, load)) {
+        if (!env_step(MODE_FAST, 1 << MODE_FAST, E, actions + e * 12, h->cfg, h->A, cache_half(step), e, gidx, flags, W, out, load)) {
             load_env(h->A, (injected && load != 0) ? h->A.inject + e * POSE_F4 : rec, e, E);
             h->last_load[(size_t)e] = load;
             int dummy;
             pool_count = 0;
-            env_step(load == 0 ? MODE_LIGHT : MODE_FULL, E, actions + e * 12, h->cfg, h->A, cache_half(step), e, gidx, flags, W, out, dummy);
+            const bool force_full = getenv("HSIM_FORCE_FULL") != nullptr; /* debugging: everything through the general path */
+            env_step(force_full ? MODE_FULL : mode_of_load(load), 31, E, actions + e * 12, h->cfg, h->A, cache_half(step), e, gidx, flags, W, out, dummy);
         }
         h->last_contacts[(size_t)e] = out.n_contacts;
         store_env(h->A, buf_next(step), e, E, out.score_dirty);

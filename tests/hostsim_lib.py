@@ -41,6 +41,7 @@ def lib():
         L.hsim_reset.argtypes = [vp, vp, C.c_int, C.c_int, u64, vp]
         L.hsim_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
         L.hsim_stats.argtypes = [vp, vp, C.c_int]
+        L.hsim_last.argtypes = [vp, vp, vp]
         L.hsim_get_state.argtypes = [vp, i64, C.POINTER(_capi.MsocEnvState)]
         L.hsim_set_state.argtypes = [vp, i64, C.POINTER(_capi.MsocEnvState)]
         _lib = L
@@ -89,6 +90,13 @@ class HostSim:
 
     def set_state(self, i: int, S: _capi.MsocEnvState) -> None:
         self._L.hsim_set_state(self._h, i, C.byref(S))
+
+    def last(self):
+        """(contacts solved, work class) of every env in the last step; class -1 = contact-free, else step_core.cuh LOAD_*."""
+        contacts = np.zeros(self.n, np.int32)
+        load = np.zeros(self.n, np.int32)
+        self._L.hsim_last(self._h, contacts.ctypes.data, load.ctypes.data)
+        return contacts, load
 
     def get_obs(self, i: int) -> np.ndarray:
         return self.obs[i].copy()

@@ -104,3 +104,41 @@ def test_global_offset_shards_agree():
         la, ha = lo.step(act[:32]), hi.step(act[32:])
         for x, y, z in zip(fa, la, ha):
             assert np.array_equal(x, np.concatenate([y, z]))
+
+
+def test_class_modes_equal_the_general_path(monkeypatch):
+    """Every work class of the contact kernel (light: one agent x wall pair; pair: one agent x agent / ball x agent pair;
+    multi: several wall pairs) solves its islands on their own.  From identical states the result must be the general
+    path's (HSIM_FORCE_FULL routes every declined env through MODE_FULL) -- bit for bit on the host build, where
+    nothing is contracted -- arbiter cache included."""
+    n = 512
+    a, b = H.HostSim(n, P.CONFIG, seed=1), H.HostSim(n, P.CONFIG, seed=1)
+    a.reset(O.MODE_FULL_RANDOM, seed=1)
+    for i in range(n):
+        s = a.get_state(i)
+        s.steps = (i * 2654435761) % 1000
+        a.set_state(i, s)
+    rng = np.random.default_rng(0)
+    for _ in range(150):
+        a.step(rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32))
+    seen = {0: 0, 1: 0, 2: 0, 3: 0}
+    for _ in range(25):
+        for i in range(n):
+            b.set_state(i, a.get_state(i))
+        act = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)
+        monkeypatch.delenv("HSIM_FORCE_FULL", raising=False)
+        out_a = a.step(act)
+        cont_a, load_a = a.last()
+        monkeypatch.setenv("HSIM_FORCE_FULL", "1")
+        out_b = b.step(act)
+        cont_b, _ = b.last()
+        monkeypatch.delenv("HSIM_FORCE_FULL", raising=False)
+        for x, y in zip(out_a, out_b):
+            assert np.array_equal(x, y)
+        assert np.array_equal(cont_a, cont_b)
+        for k in seen:
+            seen[k] += int(np.sum((load_a == k) & (cont_a > 0)))
+        for i in np.nonzero(load_a >= 0)[0]:
+            sa, sb = a.get_state(int(i)), b.get_state(int(i))
+            assert bytes(sa) == bytes(sb), (int(i), int(load_a[i]))
+    assert min(seen.values()) > 20, seen   # every class really solved contacts
