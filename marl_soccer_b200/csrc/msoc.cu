@@ -117,7 +117,7 @@ struct StepParams {
     int64_t e0, e1;       /* the envs this launch steps */
     uint64_t global_offset;
     uint32_t flags;
-    int heavy_lanes;      /* envs per warp-batch of the heavy contact kernel: 32, 16 or 8 (launch_step) */
+    int heavy_lanes;      /* envs per heavy warp-batch (MSOC_HEAVY_LANES, experiments) or 0: chosen by the contact kernel */
     int chunk;            /* -1: a whole step (list counters alternate with the step counter, the contact kernel advances it);
                              >= 0: one pipeline chunk of a host-buffer step (its own pre-zeroed counters, nobody advances) */
 };
@@ -417,7 +417,6 @@ constexpr int HEAVY_BLOCK = MSOC_HEAVY_BLOCK;
 #endif
 constexpr int HEAVY_MIN_BLOCKS = MSOC_HEAVY_MIN_BLOCKS;
 
-constexpr int64_t HEAVY_FULL_WARP_ENVS = 393216; /* ranges of at least this many envs use full-warp heavy batches */
 constexpr int HEAVY_WARP_WORDS = (32 * ENV_STRIDE + 3) & ~3; /* 16-byte aligned per-warp scratch */
 constexpr size_t STEP_SMEM_BYTES = (size_t)(HEAVY_BLOCK / 32) * HEAVY_WARP_WORDS * sizeof(float);
 
@@ -441,7 +440,17 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
     MSOC_CHECK(step >= 0 && step < 6, CHK_STEP_COUNTER);
     MSOC_CHECK(n_heavy >= 0 && n_light >= 0 && (int64_t)n_heavy + n_light <= P.e1 - P.e0, CHK_LIST_COUNT);
     MSOC_CHECK(n_multi >= 0 && n_pair >= 0 && (int64_t)n_multi + n_pair <= P.e1 - P.e0, CHK_LIST_COUNT);
-    const int b_heavy = (n_heavy + P.heavy_lanes - 1) / P.heavy_lanes;
+    /* Envs per heavy batch.  A heavy batch is bound by its latency (the warp walks the union of its lanes' divergent
+       contact work, ~50 us for one env, ~100 us for 32): as few envs per warp as still gives every heavy batch a warp of
+       its own at once; full warps when there are many times more heavy envs than warps (throughput). */
+    int heavy_lanes = P.heavy_lanes;
+    if (heavy_lanes == 0) {
+        const int n_warps_ = gridDim.x * (HEAVY_BLOCK / 32);
+        heavy_lanes = 1;
+        while (heavy_lanes < 32 && heavy_lanes * n_warps_ < n_heavy) heavy_lanes *= 2;
+        if (heavy_lanes >= 16) heavy_lanes = 32;
+    }
+    const int b_heavy = (n_heavy + heavy_lanes - 1) / heavy_lanes;
     const int b_multi = b_heavy + (n_multi + 31) / 32, b_pair = b_multi + (n_pair + 31) / 32;
     const int batches = b_pair + (n_light + 31) / 32;
 
@@ -455,15 +464,17 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
     W.geom = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST) * 32 + lane;
     W.old = s_warp + (BODY_FIELDS * 5 + CON_FIELDS * CON_FAST + GEOM_WORDS) * 32 + lane;
     W.isl = s_warp + BODY_FIELDS * 5 * 32 + lane; /* island modes: their contact slots, in the (then idle) contact pool */
+    /* A warp's first batch is its own number (so the heavy batches, numbered first, each start at once on a warp of their
+       own); the following ones are handed out by the batch counter.  (Claiming batches ahead of time and pulling their
+       state into the L2 while the current one is stepped was measured slower: batches waiting behind a long one cost
+       more than the latency that is hidden.) */
+    const int n_warps = gridDim.x * (HEAVY_BLOCK / 32);
+    int b = blockIdx.x * (HEAVY_BLOCK / 32) + warp;
 #pragma unroll 1
-    while (true) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(ctl + CTL_NEXT_BATCH, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= batches) break;
+    while (b < batches) {
         int mode, idx, count, lanes = 32;
         const int *slot;
-        if (b < b_heavy)      { mode = MODE_FULL;  lanes = P.heavy_lanes; idx = b * lanes + lane;  count = n_heavy; slot = P.list + (P.e1 - 1 - idx); }
+        if (b < b_heavy)      { mode = MODE_FULL;  lanes = heavy_lanes; idx = b * lanes + lane;  count = n_heavy; slot = P.list + (P.e1 - 1 - idx); }
         else if (b < b_multi) { mode = MODE_MULTI; idx = (b - b_heavy) * 32 + lane; count = n_multi; slot = P.list2 + (P.e1 - 1 - idx); }
         else if (b < b_pair)  { mode = MODE_PAIR;  idx = (b - b_multi) * 32 + lane; count = n_pair;  slot = P.list2 + (P.e0 + idx); }
         else                  { mode = MODE_LIGHT; idx = (b - b_pair) * 32 + lane;  count = n_light; slot = P.list + (P.e0 + idx); }
@@ -483,6 +494,8 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
         /* (obs_tile starts with a __syncwarp: the solver scratch of every lane is dead before it is reused) */
         if (mask != 0u) obs_tile(P.A, P.cfg, P.obs_out, P.frames_out, step, s_warp, mask, my_env, lane);
         MSOC_TL_END(mode == MODE_FULL ? 2 : mode == MODE_LIGHT ? 1 : 3);
+        if (lane == 0) b = n_warps + atomicAdd(ctl + CTL_NEXT_BATCH, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
     }
     flush_tally(T, P.stats, lane);
 }
@@ -726,7 +739,7 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     fill_cfg(cfg, h->cfg);
     if (const char *hl = getenv("MSOC_HEAVY_LANES")) {
         const int v = atoi(hl);
-        if (v == 8 || v == 16 || v == 32) h->heavy_lanes_override = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->heavy_lanes_override = v;
     }
     /* every failure below goes through msoc_destroy, which releases whatever exists so far */
     auto bail = [&](int code, const char *what, cudaError_t e) { msoc_destroy(h); return fail(code, what, e); };
@@ -827,10 +840,7 @@ static int launch_step(msoc_handle *h, StepParams &P, int64_t e0, int64_t e1, in
 {
     P.e0 = e0; P.e1 = e1; P.chunk = chunk;
     const int64_t m = e1 - e0;
-    /* A heavy batch is bound by its latency (the warp walks the union of its lanes' divergent contact work).  With
-       plenty of heavy envs full warps give the most throughput; when they (~1.4 % of the range) do not even occupy the
-       resident warps once, batches of fewer envs finish sooner. */
-    P.heavy_lanes = h->heavy_lanes_override ? h->heavy_lanes_override : (m >= HEAVY_FULL_WARP_ENVS ? 32 : 16);
+    P.heavy_lanes = h->heavy_lanes_override; /* 0: the contact kernel chooses by the number of heavy envs */
     msoc_step_fast_kernel<<<(unsigned)((m + FAST_BLOCK - 1) / FAST_BLOCK), FAST_BLOCK, FAST_SMEM_BYTES, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
