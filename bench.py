@@ -5,8 +5,8 @@ CPU oracle timed on the host cores as the reported baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E | --global-envs G] [--impl reference]
 
-One "step" = one msoc_step call over this rank's shard = three kernel launches (the streaming contact-free kernel over
-all envs, then the light and the heavy contact kernels side by side on two streams).  Under torchrun (N > 1) every
+One "step" = one msoc_step call over this rank's shard = two kernel launches (the streaming contact-free kernel over
+all envs, then one persistent contact kernel over the envs it declined, by work class).  Under torchrun (N > 1) every
 rank owns a contiguous range of global env indices: E envs each by default (weak scaling, BASELINE config 4's total on
 every GPU), or G / N with --global-envs G (strong scaling: BASELINE config 4 as written, 1 048 576 envs split over
 2/4/8 GPUs).  At N = 1 the line also carries BASELINE config 3 (65 536 envs, eager and as a replayed CUDA graph) and
@@ -44,7 +44,7 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """dram bytes per step (sum over the three step kernels) from the committed ncu capture, or None."""
+    """dram bytes per step (sum over the step kernels) from the committed ncu capture, or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f)
@@ -224,6 +224,29 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def bind_near_gpu(torch, dev):
+    """Pins this process to the CPUs NVML reports as local to the GPU (its NUMA node), so that the pinned host buffers
+    of the end-to-end path are allocated next to the GPU's PCIe root.  Returns (previous affinity, CPUs bound) or
+    (None, None) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(dev)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        old = os.sched_getaffinity(0)
+        cpus = sorted(set(cpus) & set(old))
+        if not cpus:
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return old, len(cpus)
+    except Exception:
+        return None, None
+
+
+
 def make_pool(torch, np, n, dev, seed):
     """Actions: one flat device buffer of 16*N*12 uniform(-1,1) floats generated before the timed region; step k reads
     the window starting at a pseudo-random env offset r_k, so every env sees an effectively i.i.d. action stream (a
@@ -254,7 +277,7 @@ def preroll(torch, sim, pool, cfg, steps, _capi):
 
 def config3_record(torch, np, _capi, cfg, dev, peak):
     """BASELINE config 3: 65 536 envs on one GPU, auto-reset, shaped rewards.  The working set (~110 MB) sits in the
-    126 MB L2, and the step is three short launches: eager launches expose the launch latency, a replayed CUDA graph
+    126 MB L2, and the step is two short launches: eager launches expose the launch latency, a replayed CUDA graph
     of 20 steps (the device-side step counter makes any capture length replayable) shows the kernels themselves."""
     from marl_soccer_b200.sim import BatchedSoccerSim
     n = 65536
@@ -430,13 +453,14 @@ def main():
     stats = dict(zip([k for k, _ in _capi.MsocStats._fields_], stats_t.cpu().tolist()))
     total_envs = int(sum_over_ranks(torch, dist, dev, n))
 
-    # device time of one step on this rank (three launches; events bracket K back-to-back steps)
+    # device time of one step on this rank (two launches; events bracket K back-to-back steps)
     kernel_ms = e0.elapsed_time(e1) / args.steps
     value = total_envs * args.steps / (elapsed_ms * 1e-3)
 
     # end to end through the host-buffer C-ABI calls: pinned host actions in, pinned host results out, copies inside the
     # timed region.  Primary: msoc_step_host_frames (the newest frame per agent comes back, 352 B/env; the caller owns
     # the 3-frame stack as soccer_env.py:130-140 does).  Also: msoc_step_host (the full stacked observation).
+    old_affinity, near_cpus = bind_near_gpu(torch, dev)
     h_acts = [torch.empty((n, 4, 3), dtype=torch.float32).pin_memory().copy_(pool[7 + j].cpu()) for j in range(4)]
     h_obs = torch.empty((n, 4, 66), dtype=torch.float32).pin_memory()
     h_frames = torch.empty((n, 4, 22), dtype=torch.float32).pin_memory()
@@ -470,6 +494,8 @@ def main():
         return total_envs * args.e2e_steps / float(tt.item())
     e2e_frames = time_host(host_step_frames)
     e2e_full = time_host(host_step_full)
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)  # the CPU baseline below uses every core again
     h2d = n * 12 * 4
     small = n * (2 * 4 + 1 + 1 + 2 * 4)
     d2h_frames, d2h_full = n * 4 * 22 * 4 + small, n * 4 * 66 * 4 + small
@@ -513,12 +539,12 @@ def main():
                      "traffic_note": "DRAM bytes of one 1 Mi-env step from the committed ncu capture (profiles/traffic.json); below the "
                                      "algorithmic bytes because the observation history is rebuilt from 128-byte state records instead of read back",
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
-                     "kernel": "msoc_step = msoc_step_fast_kernel + msoc_step_light_kernel || msoc_step_contact_kernel "
-                               "(whole step: algorithmic bytes of all envs / device time of the three launches)",
+                     "kernel": "msoc_step = msoc_step_fast_kernel + msoc_step_contact_kernel "
+                               "(whole step: algorithmic bytes of all envs / device time of the two launches)",
                      "kernel_ms": kernel_ms},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_frames, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_frames,
-                "steps": args.e2e_steps, "api": "msoc_step_host_frames (pinned host buffers; newest frame per agent, the caller owns the stack)",
+                "steps": args.e2e_steps, "host_cpus_near_gpu": near_cpus, "api": "msoc_step_host_frames (pinned host buffers; newest frame per agent, the caller owns the stack)",
                 "full_observation": {"value": e2e_full, "d2h_bytes_per_step": d2h_full, "api": "msoc_step_host ((N,4,66) stacked observation)"}},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round measurement on a B200 box (run through gpurun): tests, full bench, reference arm, ncu launch list
-# and one ncu --set full capture of one whole step (its three kernels).  Outputs land in gpurun_out/.
+# and one ncu --set full capture of one whole step (its two kernels).  Outputs land in gpurun_out/.
 set -u
 TAG=${1:-r02}
 mkdir -p gpurun_out
@@ -14,8 +14,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_
 # the bench workload itself (same 1000-step pre-roll, so the same steady-state env mix), fewer timed steps
 SHORT="python bench.py --steps 40 --warmup 5 --e2e-steps 2 --no-cpu-baseline --no-extras"
 $SHORT > gpurun_out/${TAG}_short_plain.json 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:msoc_step -s 3030 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:msoc_step -s 2020 -c 40 --csv --log-file gpurun_out/${TAG}_launches.csv $SHORT > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $SHORT > gpurun_out/${TAG}_short_plain2.json 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:msoc_step -s 3030 -c 3 -o gpurun_out/${TAG}_step_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:msoc_step -s 2020 -c 2 -f -o gpurun_out/${TAG}_step_full $SHORT > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log
 ls -la gpurun_out | tail -15

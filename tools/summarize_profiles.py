@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turns the raw outputs of tools/gpu_measure.sh (gpurun_out/<tag>_*) into the committed summaries under
-profiles/: bench lines, ncu launch list, the key metrics of the ncu --set full capture of one step (its three kernels)
+profiles/: bench lines, ncu launch list, the key metrics of the ncu --set full capture of one step (its two kernels)
 and profiles/traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic)."""
 import csv
 import json
@@ -56,7 +56,7 @@ with open(os.path.join(P, f"{tag}_step_kernel_ncu_full.txt"), "w") as f:
 def to_bytes(unit, v):
     m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     return float(v) * m[unit]
-# one step = the three captured launches (fast, heavy contact, light): DRAM traffic of the step = their sum
+# one step = the two captured launches (fast, contact): DRAM traffic of the step = their sum
 rd = sum(to_bytes(*L["dram__bytes_read.sum"]) for L in launches)
 wr = sum(to_bytes(*L["dram__bytes_write.sum"]) for L in launches)
 n = short["config"]["envs_per_gpu"]
