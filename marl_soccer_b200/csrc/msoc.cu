@@ -232,13 +232,25 @@ __device__ __forceinline__ void obs_fetch(const Arrays &A, int step, uint32_t ma
     }
 }
 __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, float *obs_out, float *frames_out, int step, float *s_stage,
-                                         uint32_t mask, int64_t my_env64, int lane)
+                                         uint32_t lane_mask, int64_t my_env64, int lane)
 {
-    const int my_env = (int)my_env64; /* a handle holds fewer than 2^31 envs */
     const int a = lane & 3, el = lane >> 2;
     float4 *recs4 = reinterpret_cast<float4 *>(s_stage + BLOCK_WORDS);
     float2 *mine = reinterpret_cast<float2 *>(s_stage) + lane * 33; /* row (el, a) of the staged blocks */
     __syncwarp(); /* the siblings' stores of the new records are ordered before the loads below */
+    /* the envs of the lanes in lane_mask, compacted: the streaming kernel's warps have ~23 of 32 (the others were declined),
+       which is three groups of eight instead of four */
+    uint32_t mask = lane_mask;
+    int my_env = (int)my_env64; /* a handle holds fewer than 2^31 envs */
+    if (lane_mask != 0xffffffffu) {
+        int *s_idx = reinterpret_cast<int *>(s_stage);
+        if ((lane_mask >> lane) & 1u) s_idx[__popc(lane_mask & ((1u << lane) - 1u))] = my_env;
+        __syncwarp();
+        const int cnt = __popc(lane_mask);
+        my_env = lane < cnt ? s_idx[lane] : 0;
+        mask = (1u << cnt) - 1u; /* cnt < 32 here */
+        __syncwarp();
+    }
     int g = __ffs((int)((mask & 0xffu ? 1u : 0u) | (mask & 0xff00u ? 2u : 0u) | (mask & 0xff0000u ? 4u : 0u) | (mask & 0xff000000u ? 8u : 0u))) - 1;
     RecLoad R;
     obs_fetch(A, step, mask, g, my_env, lane, R);
