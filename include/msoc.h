@@ -149,9 +149,8 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
                              any auto-reset (game/game.py:415); may be NULL
    flags: MSOC_STEP_AUTO_RESET.
    Stream semantics: asynchronous; everything is ordered after the work already enqueued on `stream`, and work
-   enqueued on `stream` afterwards sees the complete step.  One step is three kernel launches (a streaming
-   contact-free kernel over all envs, then two contact kernels side by side); the handle runs one of them on an
-   internal stream that is forked from and joined back into `stream` with events.  Which half of the ping-pong state
+   enqueued on `stream` afterwards sees the complete step.  One step is two kernel launches on `stream` (a streaming
+   contact-free kernel over all envs, then one persistent contact kernel over the envs it declined).  Which half of the ping-pong state
    is current is a counter in device memory that the kernels advance themselves, so a CUDA graph may capture any
    number of consecutive steps and be replayed any number of times. */
 int msoc_step(msoc_handle *h, const float *d_actions, float *d_obs_out,

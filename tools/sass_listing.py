@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""profiles/<tag>_sass_{fast,light,contact}.txt: SASS of the three step kernels of marl_soccer_b200/libmsoc.so
+"""profiles/<tag>_sass_{fast,contact}.txt: SASS of the two step kernels of marl_soccer_b200/libmsoc.so
 (cuobjdump -sass), each preceded by its mnemonic histogram and the lines that prove the Blackwell-specific paths
 (UBLKCP = cp.async.bulk, FENCE.VIEW.ASYNC, UTMACMDFLUSH).  Encodings are stripped to keep the files readable."""
 import collections, os, re, subprocess, sys
@@ -8,7 +8,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 lib = os.path.join(ROOT, "marl_soccer_b200", "libmsoc.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 blocks = re.split(r"(?=\t*Function : )", sass)
-for name in ("fast", "light", "contact"):
+for name in ("fast", "contact"):
     blk = next(b for b in blocks if f"msoc_step_{name}_kernel" in b.split("\n", 1)[0])
     lines = []
     for ln in blk.splitlines():
