@@ -444,6 +444,7 @@ def main():
         dist.all_reduce(stats_t)  # the only collective: one 64-byte sum per rollout
     e1.record()
     torch.cuda.synchronize(dev)
+    classes = sim.class_counts()  # work classes of the last timed step on this rank (instrumentation)
     if dist is not None:
         dist.barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -559,6 +560,7 @@ def main():
                 "steps": args.e2e_steps, "host_cpus_near_gpu": near_cpus, "api": "msoc_step_host_frames (pinned host buffers; newest frame per agent, the caller owns the stack)",
                 "full_observation": {"value": e2e_full, "d2h_bytes_per_step": d2h_full, "api": "msoc_step_host ((N,4,66) stacked observation)"}},
         "gpu_launches": int(launches),
+        "class_mix_last_step": {**{k: v / n for k, v in classes.items()}, "contact_free": 1.0 - sum(classes.values()) / n},
         "clocks": clocks,
         "stats": stats,
     }

@@ -203,6 +203,12 @@ int msoc_get_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, float *h_
 int msoc_stats_device(msoc_handle *h, double *d_out, int reset, void *stream);
 int msoc_stats_read(msoc_handle *h, msoc_stats *h_out, int reset, void *stream);
 
+/* Work classes of the last step (instrumentation for tests and bench.py; no counterpart in the reference): how many envs
+   the streaming kernel handed to the contact kernel as light (exactly one agent x wall candidate pair), heavy (the
+   general path), pair (exactly one agent x agent / ball x agent pair) and multi (several wall pairs), in this order.
+   The rest of the envs were contact-free.  Stream-ordered read, then synchronises `stream`. */
+int msoc_last_class_counts(msoc_handle *h, int32_t h_out[4], void *stream);
+
 /* Launch accounting for bench.py: number of kernels this library has launched. */
 uint64_t msoc_launch_count(void);
 

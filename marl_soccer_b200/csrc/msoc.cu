@@ -61,7 +61,7 @@ constexpr int MAX_CHUNKS = 8; /* pipeline stages of the host-buffer step */
 /* control block in device memory (ints): two sets of list counters that alternate between steps, the step counters
    that select the ping-pong halves, one set of list counters per pipeline chunk of the host-buffer step */
 enum { CTL_LIGHT = 0, CTL_HEAVY = 1, CTL_NEXT_BATCH = 2, CTL_PAIR = 4, CTL_MULTI = 5, CTL_WORDS = 8 };
-enum { CTL_STEP_FAST = 16, CTL_STEP_CONTACT = 17, CTL_CHUNK0 = 24, CTL_TOTAL = CTL_CHUNK0 + CTL_WORDS * MAX_CHUNKS };
+enum { CTL_STEP_FAST = 16, CTL_STEP_CONTACT = 17, CTL_LAST_COUNTS = 20 /* light, heavy, pair, multi of the last step */, CTL_CHUNK0 = 24, CTL_TOTAL = CTL_CHUNK0 + CTL_WORDS * MAX_CHUNKS };
 
 struct msoc_handle {
     int device;
@@ -445,7 +445,11 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
     const int step = P.ctl[CTL_STEP_CONTACT];
     int *ctl = step_ctl(P, step);
     /* this step's fast kernel is complete and the next one starts after this kernel: advance the step counter */
-    if (P.chunk < 0 && blockIdx.x == 0 && tid == 0) P.ctl[CTL_STEP_FAST] = (step + 1) % 6;
+    if (P.chunk < 0 && blockIdx.x == 0 && tid == 0) {
+        P.ctl[CTL_STEP_FAST] = (step + 1) % 6;
+        P.ctl[CTL_LAST_COUNTS + 0] = ctl[CTL_LIGHT]; P.ctl[CTL_LAST_COUNTS + 1] = ctl[CTL_HEAVY];
+        P.ctl[CTL_LAST_COUNTS + 2] = ctl[CTL_PAIR]; P.ctl[CTL_LAST_COUNTS + 3] = ctl[CTL_MULTI];
+    }
     /* final: the fast kernel has finished */
     const int n_heavy = (MODES & (1 << MODE_FULL)) ? ctl[CTL_HEAVY] : 0, n_multi = (MODES & (1 << MODE_MULTI)) ? ctl[CTL_MULTI] : 0;
     const int n_pair = (MODES & (1 << MODE_PAIR)) ? ctl[CTL_PAIR] : 0, n_light = (MODES & (1 << MODE_LIGHT)) ? ctl[CTL_LIGHT] : 0;
@@ -525,8 +529,17 @@ __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_conta
     contact_body<MSOC_CONTACT_MODES>(P, s_pool_count);
 }
 
-/* advances the step counter after a chunked host-buffer step (whose contact kernels do not) */
-__global__ void msoc_advance_kernel(int *ctl) { ctl[CTL_STEP_FAST] = (ctl[CTL_STEP_FAST] + 1) % 6; }
+/* after a chunked host-buffer step (whose contact kernels do not): advances the step counter, sums the chunks' class counts */
+__global__ void msoc_advance_kernel(int *ctl)
+{
+    if (threadIdx.x == 0) ctl[CTL_STEP_FAST] = (ctl[CTL_STEP_FAST] + 1) % 6;
+    if (threadIdx.x < 4) {
+        const int word = threadIdx.x == 0 ? CTL_LIGHT : threadIdx.x == 1 ? CTL_HEAVY : threadIdx.x == 2 ? CTL_PAIR : CTL_MULTI;
+        int sum = 0;
+        for (int c = 0; c < MAX_CHUNKS; c++) sum += ctl[CTL_CHUNK0 + CTL_WORDS * c + word];
+        ctl[CTL_LAST_COUNTS + threadIdx.x] = sum;
+    }
+}
 
 /* ------------------------------------------------------------------------------------- reset */
 struct ResetParams {
@@ -937,7 +950,7 @@ static int step_host_impl(msoc_handle *h, const float *h_actions, float *h_obs, 
     }
     CUDA_TRY(cudaEventRecord(h->ev_pipe_join, h->pipe_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_pipe_join, 0));
-    msoc_advance_kernel<<<1, 1, 0, st>>>(h->d_ctl);
+    msoc_advance_kernel<<<1, 32, 0, st>>>(h->d_ctl);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1106,6 +1119,16 @@ int msoc_stats_device(msoc_handle *h, double *d_out, int reset, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(d_out, h->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (reset) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(double), st));
+    return MSOC_OK;
+}
+
+int msoc_last_class_counts(msoc_handle *h, int32_t h_out[4], void *stream)
+{
+    if (!h || !h_out) return fail(MSOC_ERR_INVALID, "msoc_last_class_counts: null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h_out, h->d_ctl + CTL_LAST_COUNTS, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return MSOC_OK;
 }
 

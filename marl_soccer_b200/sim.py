@@ -125,6 +125,12 @@ class BatchedSoccerSim:
         t = self.stats_tensor(reset).cpu().tolist()
         return dict(zip([k for k, _ in _capi.MsocStats._fields_], t))
 
+    def class_counts(self) -> dict:
+        """Work classes of the last step (instrumentation): envs handed to the contact kernel per class."""
+        out = (C.c_int32 * 4)()
+        _capi.check(self._L.msoc_last_class_counts(self._h, C.byref(out), self._stream()))
+        return {"light": out[0], "heavy": out[1], "pair": out[2], "multi": out[3]}
+
     def get_states(self, idx) -> list:
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         arr = (_capi.MsocEnvState * len(idx))()

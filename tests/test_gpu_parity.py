@@ -1,4 +1,6 @@
 """Parity of the CUDA kernels (through the C-ABI, include/msoc.h) with the CPU oracle.  -m gpu."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -163,6 +165,7 @@ def test_chunked_host_step_equals_the_whole_step():
     assert np.array_equal(a, b.cpu().numpy())
     rng = np.random.default_rng(1)
     stack = a.copy()
+    seen = {}
     for t in range(12):
         act = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)
         o_h, r_h, d_h, g_h = host.step(act)
@@ -170,6 +173,14 @@ def test_chunked_host_step_equals_the_whole_step():
         assert np.array_equal(o_h, o_d.cpu().numpy()) and np.array_equal(r_h, r_d.cpu().numpy()), t
         assert np.array_equal(d_h, d_d.cpu().numpy()) and np.array_equal(g_h, g_d.cpu().numpy()), t
         assert np.array_equal(host.score, dev.score.cpu().numpy()), t
+        # the contact kernel's four work classes all occur, and the chunks of the host step add up to the device step's
+        cc = dev.class_counts()
+        assert sum(cc.values()) < n, cc
+        for k, v in cc.items():
+            seen[k] = seen.get(k, 0) + v
+        hc = (C.c_int32 * 4)()
+        _capi.check(_capi.lib().msoc_last_class_counts(host._h, C.byref(hc), None))
+        assert list(hc) == [cc["light"], cc["heavy"], cc["pair"], cc["multi"]], (list(hc), cc)
         # frames-only variant: the caller keeps the 3-frame stack (soccer_env.py:130-140, :92-96)
         frames, r_f, d_f, g_f = fr.step_frames(act)
         s4 = stack.reshape(n, 4, 3, 22)
@@ -179,6 +190,7 @@ def test_chunked_host_step_equals_the_whole_step():
         assert np.array_equal(stack, o_h), t
         assert np.array_equal(r_f, r_h) and np.array_equal(d_f, d_h) and np.array_equal(g_f, g_h)
     assert d_h.sum() == 0 and host.stats()["episodes"] == n  # everybody truncated once, at step 9
+    assert min(seen.values()) > 1000, seen  # (the corner spawns of the first steps are all multi / heavy; light comes later)
 
 
 def test_ragged_sizes_and_masked_reset():
