@@ -516,17 +516,10 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
     flush_tally(T, P.stats, lane);
 }
 
-#ifdef MSOC_CONTACT_MAXNREG
-__global__ void __maxnreg__(MSOC_CONTACT_MAXNREG) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
-#else
 __global__ void __launch_bounds__(HEAVY_BLOCK, HEAVY_MIN_BLOCKS) msoc_step_contact_kernel(const __grid_constant__ StepParams P)
-#endif
 {
     __shared__ int s_pool_count[HEAVY_BLOCK / 32];
-#ifndef MSOC_CONTACT_MODES
-#define MSOC_CONTACT_MODES ((1 << MODE_FULL) | (1 << MODE_LIGHT) | (1 << MODE_PAIR) | (1 << MODE_MULTI))
-#endif
-    contact_body<MSOC_CONTACT_MODES>(P, s_pool_count);
+    contact_body<(1 << MODE_FULL) | (1 << MODE_LIGHT) | (1 << MODE_PAIR) | (1 << MODE_MULTI)>(P, s_pool_count);
 }
 
 /* after a chunked host-buffer step (whose contact kernels do not): advances the step counter, sums the chunks' class counts */
@@ -809,8 +802,6 @@ int msoc_create(const msoc_config *cfg, int64_t n_envs, int device, uint64_t see
     ce = cudaFuncSetAttribute(msoc_step_contact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM_BYTES);
     if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM_BYTES);
-    if (const char *cv = getenv("MSOC_FAST_CARVEOUT")) /* experiments: shared-memory carve-out (percent) of the streaming kernel */
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(msoc_step_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
     if (ce != cudaSuccess) return bail(MSOC_ERR_CUDA, "msoc_create: smem attribute", ce);
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, msoc_step_contact_kernel, HEAVY_BLOCK, STEP_SMEM_BYTES);
