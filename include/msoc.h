@@ -45,6 +45,8 @@ typedef enum {
 
 /* step flags */
 #define MSOC_STEP_AUTO_RESET 1u /* marl_vecenv.py:45-53: reset finished envs in full-random mode */
+#define MSOC_STEP_GENERAL_PATH 2u /* debugging / tests: every env that touches something goes through the general contact
+                                     path (no light / pair / multi class); same simulation, slower */
 
 /* config.json keys (config.json:1-22; readers: soccer_env.py:63-64, game/entities.py:11-17,62-67,
    game/game.py:27,262-264,330-372,430).  Absent keys take the reference's defaults in the
@@ -147,7 +149,7 @@ int msoc_reset(msoc_handle *h, const uint8_t *d_mask, int mode, int has_seed, ui
      d_goal    (N) i8        +1 blue scored, -1 red scored, 0 none (info["goal_scored_by"])
      d_score   (N,2) i32     info["score"] of this step = (blue, red) after the goal test and before
                              any auto-reset (game/game.py:415); may be NULL
-   flags: MSOC_STEP_AUTO_RESET.
+   flags: MSOC_STEP_AUTO_RESET, MSOC_STEP_GENERAL_PATH.
    Stream semantics: asynchronous; everything is ordered after the work already enqueued on `stream`, and work
    enqueued on `stream` afterwards sees the complete step.  One step is two kernel launches on `stream` (a streaming
    contact-free kernel over all envs, then one persistent contact kernel over the envs it declined).  Which half of the ping-pong state

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("MSOC_LIB", os.path.join(PKG_DIR, "libmsoc.so"))  # MS
 N_AGENTS, ACT_DIM, FRAME, STACK, OBS, MAX_CACHE = 4, 3, 22, 3, 66, 32
 MODE_RANDOM, MODE_FIXED, MODE_FULL_RANDOM = 0, 1, 2
 STEP_AUTO_RESET = 1
+STEP_GENERAL_PATH = 2  # debugging / tests: no light / pair / multi class
 
 # every symbol include/msoc.h declares (tests check that the library exports all of them)
 EXPORTS = (

@@ -1124,7 +1124,7 @@ MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *ac
             /* work class for the contact lists */
             const uint32_t dyn = m_aa | (m_ba << 6);
             const int n_as = popc32(m_as), n_dyn = popc32(dyn), n_bw = popc32(m_bw);
-            if (E.flags & FLAG_INJECT) load = LOAD_HEAVY;
+            if ((E.flags & FLAG_INJECT) || (step_flags & 2u)) load = LOAD_HEAVY; /* 2u: MSOC_STEP_GENERAL_PATH */
             else if (n_dyn == 0) {
                 if (n_as == 1 && n_bw == 0) load = LOAD_LIGHT;
                 else {

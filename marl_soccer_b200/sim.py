@@ -102,16 +102,18 @@ class BatchedSoccerSim:
                                        self._stream()))
         return self.obs
 
-    def step(self, actions: torch.Tensor, auto_reset: bool = True):
+    def step(self, actions: torch.Tensor, auto_reset: bool = True, general_path: bool = False):
         """One env-step for every env.  actions: (N, 4, 3) float32 CUDA tensor in [-1, 1] (clipped on
-        the device like soccer_env.py:119)."""
+        the device like soccer_env.py:119).  general_path (debugging / tests): every env that touches something is
+        stepped by the general contact path instead of its work class's own."""
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
         if actions.numel() != self.num_envs * 12:
             raise ValueError(f"actions must have shape ({self.num_envs}, 4, 3), got {tuple(actions.shape)}")
         _capi.check(self._L.msoc_step(self._h, actions.data_ptr(), self.obs.data_ptr(),
                                       self.reward.data_ptr(), self.done.data_ptr(), self.goal.data_ptr(),
-                                      self.score.data_ptr(), _capi.STEP_AUTO_RESET if auto_reset else 0,
+                                      self.score.data_ptr(),
+                                      (_capi.STEP_AUTO_RESET if auto_reset else 0) | (_capi.STEP_GENERAL_PATH if general_path else 0),
                                       self._stream()))
         return self.obs, self.reward, self.done, self.goal
 
