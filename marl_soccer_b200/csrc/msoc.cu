@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
 
 /* Per-warp scratch of 32 x ENV_STRIDE floats: during the contact solve it holds the lanes' solver bodies (30 fields,
    field-major with stride 32: conflict-free), the warp's pool of 32 x CON_FAST contact records (15 fields, field-major;
-   an env takes as many records as it has contacts), the parked poses and the preloaded arbiter cache entries;
-   afterwards the staged observation blocks. */
+   an env takes as many records as it has contacts; in the pair / multi modes the same words are the lanes' own island
+   slots), the parked poses and the preloaded arbiter cache entries; afterwards the staged observation blocks. */
 static_assert(STAGE_WORDS <= 32 * ENV_STRIDE, "the observation staging must fit the per-warp solver scratch");
 #ifndef MSOC_HEAVY_BLOCK
 #define MSOC_HEAVY_BLOCK 64 /* threads per block of the contact kernel */
@@ -457,7 +457,7 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
     MSOC_CHECK(n_heavy >= 0 && n_light >= 0 && (int64_t)n_heavy + n_light <= P.e1 - P.e0, CHK_LIST_COUNT);
     MSOC_CHECK(n_multi >= 0 && n_pair >= 0 && (int64_t)n_multi + n_pair <= P.e1 - P.e0, CHK_LIST_COUNT);
     /* Envs per heavy batch.  A heavy batch is bound by its latency (the warp walks the union of its lanes' divergent
-       contact work, ~50 us for one env, ~100 us for 32): as few envs per warp as still gives every heavy batch a warp of
+       contact work: 24 us median / 65 us worst for one env, ~110 us median for 32): as few envs per warp as still gives every heavy batch a warp of
        its own at once; full warps when there are many times more heavy envs than warps (throughput). */
     int heavy_lanes = P.heavy_lanes;
     if (heavy_lanes == 0) {
