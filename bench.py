@@ -365,8 +365,8 @@ def config5_record(torch, _capi, cfg, dev, world_note="per GPU"):
     ms = e0.elapsed_time(e1)
     st = sim.stats()
     sim.close()
-    return {"workload": f"BASELINE config 5: PPO rollout, {n} envs x {T} steps {world_note}, MLP policy (bf16 autocast) and "
-                        "normaliser in the loop, one CUDA graph per rollout",
+    return {"workload": f"BASELINE config 5: PPO rollout, {n} envs x {T} steps {world_note}, MLP policy (bf16, both nets packed into batched "
+                        "GEMMs), normaliser (one fused pass per step) in the loop, one CUDA graph per rollout",
             "env_steps_per_s": n * T * R / (ms * 1e-3), "ms_per_rollout_step": ms / (T * R), "episodes": st["episodes"]}
 
 

@@ -205,6 +205,20 @@ int msoc_get_obs_host(msoc_handle *h, const int64_t *h_idx, int64_t n, float *h_
 int msoc_stats_device(msoc_handle *h, double *d_out, int reset, void *stream);
 int msoc_stats_read(msoc_handle *h, msoc_stats *h_out, int reset, void *stream);
 
+/* Rollout half of the trainer (marl-soccer.ipynb:366-431), the immediate caller of msoc_step: what the loop does with the
+   blue agents' observations before the policy runs, as ONE pass over them instead of five torch passes.
+     d_obs      (N,4,66) f32   the stacked observation msoc_step wrote; rows 0,1 of every env (the trainable agents) are read
+     d_shift, d_inv_std (66) f32   normaliser in multiply-add form: x' = clip(x * inv_std + shift, -10, 10)
+                                   (shift = -mean / (std + 1e-8), inv_std = 1 / (std + 1e-8); marl-soccer.ipynb:385)
+     d_x_out    (2N,72) bf16   normalised policy input, rows padded from 66 to 72 columns (columns 66..71 are not written:
+                               allocate zeroed); row 2e + a = agent a of env e
+     d_raw_out  (N,2,66) bf16  the raw observation for the rollout buffer (marl-soccer.ipynb:403), or NULL
+     d_moments  (2,66) f64     per-feature sum and sum of squares of the raw rows are ADDED here (running mean / variance
+                               of the normaliser, marl-soccer.ipynb:264-296, :431), or NULL
+   Runs on the current device, asynchronous on `stream`. */
+int msoc_policy_inputs(const float *d_obs, int64_t n_envs, const float *d_shift, const float *d_inv_std, void *d_x_out,
+                       void *d_raw_out, double *d_moments, void *stream);
+
 /* Work classes of the last step (instrumentation for tests and bench.py; no counterpart in the reference): how many envs
    the streaming kernel handed to the contact kernel as light (exactly one agent x wall candidate pair), heavy (the
    general path), pair (exactly one agent x agent / ball x agent pair) and multi (several wall pairs), in this order.

@@ -22,7 +22,7 @@ EXPORTS = (
     "msoc_last_error", "msoc_version", "msoc_create", "msoc_destroy", "msoc_num_envs", "msoc_reset",
     "msoc_step", "msoc_step_host", "msoc_reset_host", "msoc_read_counters", "msoc_get_state",
     "msoc_set_state", "msoc_get_obs_host", "msoc_step_host_frames", "msoc_stats_device", "msoc_stats_read",
-    "msoc_launch_count", "msoc_device_buffers", "msoc_debug_errors", "msoc_last_class_counts",
+    "msoc_launch_count", "msoc_device_buffers", "msoc_debug_errors", "msoc_last_class_counts", "msoc_policy_inputs",
 )
 
 
@@ -115,6 +115,7 @@ def declare(L) -> None:
     L.msoc_stats_device.argtypes = [vp, vp, C.c_int, vp]
     L.msoc_stats_read.argtypes = [vp, C.POINTER(MsocStats), C.c_int, vp]
     L.msoc_last_class_counts.argtypes = [vp, C.POINTER(C.c_int32 * 4), vp]
+    L.msoc_policy_inputs.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
 
 
 def lib():

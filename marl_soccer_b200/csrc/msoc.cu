@@ -15,6 +15,7 @@
  * There is no CPU fallback in this library: every entry point needs a CUDA device.
  */
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -693,6 +694,38 @@ __global__ void msoc_init_kernel(Arrays A, uint64_t seed)
     A.spawn_count[e] = 0;
 }
 
+/* ------------------------------------------------------------------ rollout: policy inputs */
+/* One pass over the blue agents' observation rows (528 contiguous bytes per env): normalised + clipped bf16 policy input
+   (padded rows), raw bf16 copy for the rollout buffer, per-feature sum / sum of squares for the running normaliser.
+   Thread (x, y): float2 x of the 132 floats of env y (+ 4 per iteration), so a thread always sees the same two features. */
+constexpr int PI_X = 66, PI_Y = 4, PI_PAD = 72;
+__global__ void __launch_bounds__(PI_X * PI_Y) msoc_policy_inputs_kernel(const float *__restrict__ obs, int64_t n, const float *__restrict__ shift,
+                                                                         const float *__restrict__ inv_std, __nv_bfloat162 *__restrict__ x_out,
+                                                                         __nv_bfloat162 *__restrict__ raw_out, double *moments)
+{
+    __shared__ float s_red[PI_Y][PI_X][4];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int row = x >= 33 ? 1 : 0, f = 2 * x - 66 * row; /* features f, f + 1 of agent `row` */
+    const float sh0 = shift[f], sh1 = shift[f + 1], is0 = inv_std[f], is1 = inv_std[f + 1];
+    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+    for (int64_t e = (int64_t)blockIdx.x * PI_Y + y; e < n; e += (int64_t)gridDim.x * PI_Y) {
+        const float2 v = reinterpret_cast<const float2 *>(obs + e * (4 * OBS))[x];
+        const float a = fminf(fmaxf(fmaf(v.x, is0, sh0), -10.0f), 10.0f), b = fminf(fmaxf(fmaf(v.y, is1, sh1), -10.0f), 10.0f);
+        x_out[((2 * e + row) * PI_PAD + f) >> 1] = __floats2bfloat162_rn(a, b);
+        if (raw_out != nullptr) raw_out[(e * (2 * OBS) + 2 * x) >> 1] = __floats2bfloat162_rn(v.x, v.y);
+        s0 += v.x; s1 += v.y; q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+    }
+    if (moments == nullptr) return;
+    s_red[y][x][0] = s0; s_red[y][x][1] = s1; s_red[y][x][2] = q0; s_red[y][x][3] = q1;
+    __syncthreads();
+    if (y == 0) {
+        double t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0;
+        for (int k = 0; k < PI_Y; k++) { t0 += s_red[k][x][0]; t1 += s_red[k][x][1]; u0 += s_red[k][x][2]; u1 += s_red[k][x][3]; }
+        atomicAdd(moments + f, t0); atomicAdd(moments + f + 1, t1);
+        atomicAdd(moments + OBS + f, u0); atomicAdd(moments + OBS + f + 1, u1);
+    }
+}
+
 /* ---------------------------------------------------------------------------------- C-ABI */
 extern "C" {
 
@@ -1110,6 +1143,21 @@ int msoc_stats_device(msoc_handle *h, double *d_out, int reset, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpyAsync(d_out, h->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (reset) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, 8 * sizeof(double), st));
+    return MSOC_OK;
+}
+
+int msoc_policy_inputs(const float *d_obs, int64_t n_envs, const float *d_shift, const float *d_inv_std, void *d_x_out,
+                       void *d_raw_out, double *d_moments, void *stream)
+{
+    if (!d_obs || !d_shift || !d_inv_std || !d_x_out || n_envs <= 0) return fail(MSOC_ERR_INVALID, "msoc_policy_inputs: bad argument");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t want = (n_envs + PI_Y - 1) / PI_Y, cap = (int64_t)sms * 7; /* 7 blocks of 264 threads per SM; a thread sums n / (4 * grid) rows in fp32 */
+    msoc_policy_inputs_kernel<<<(unsigned)(want < cap ? want : cap), dim3(PI_X, PI_Y), 0, (cudaStream_t)stream>>>(
+        d_obs, n_envs, d_shift, d_inv_std, (__nv_bfloat162 *)d_x_out, (__nv_bfloat162 *)d_raw_out, d_moments);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     return MSOC_OK;
 }
 

@@ -16,6 +16,8 @@ import torch
 import torch.nn as nn
 from torch.distributions.normal import Normal
 
+from . import _capi
+
 
 def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
     torch.nn.init.orthogonal_(layer.weight, std)
@@ -67,7 +69,12 @@ class RunningMeanStd:
 
     def update(self, x: torch.Tensor) -> None:
         x = x.reshape(-1, self.mean.shape[-1]).to(torch.float64)
-        batch_mean, batch_var, n = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        batch_var, batch_mean = torch.var_mean(x, dim=0, unbiased=False)  # one Welford pass
+        self.update_from_moments(batch_mean, batch_var, x.shape[0])
+
+    def update_from_moments(self, batch_mean: torch.Tensor, batch_var: torch.Tensor, n: int) -> None:
+        """Parallel-variance merge of one batch given by its mean, biased variance and size (marl-soccer.ipynb:275-296)."""
+        batch_mean, batch_var = batch_mean.to(torch.float64), batch_var.to(torch.float64)
         delta = batch_mean - self.mean
         tot = self.count + n
         self.mean = self.mean + delta * (n / tot)
@@ -99,6 +106,74 @@ class RolloutBuffer:
         self.rewards = torch.zeros((T, N, 2), device=device)
         self.dones = torch.zeros((T, N, 2), device=device)
         self.values = torch.zeros((T, N, 2), device=device)
+
+
+class PackedPolicy:
+    """Inference-only packing of an `Agent`'s two MLPs for the rollout loop -- the same layers in `dtype` (bf16) with
+    fp32 accumulation, laid out for the tensor cores (what the plain modules cost per step at 524 288 rows, under ncu, in
+    brackets):
+      * the first layer of both nets is ONE GEMM over inputs padded from 66 to 72 features (rows of 16-byte multiples;
+        with K = 66 cuBLAS falls back to a legacy mma.sync kernel [0.5 ms per net]);
+      * the hidden and output layers of the two nets are batched GEMMs over a (2, rows, width) stack: half the launches,
+        one tanh pass per layer instead of two;
+      * biases ride in the GEMMs: every layer's output has 8 extra channels, the first of which is the constant 1
+        (tanh of a pre-activation of 20), and the next layer's weight matrix carries its bias in that column -- a batched
+        GEMM has no bias epilogue, and `baddbmm` materialises the broadcast bias with a strided copy [0.8 ms].
+    `refresh()` re-reads the agent's parameters (call it after every optimiser step)."""
+
+    IN = 72
+    PAD = 8       # extra channels per layer: [1, 0, 0, 0, 0, 0, 0, 0]
+    ONE = 20.0    # tanh(20) == 1 in fp32 and bf16
+
+    def __init__(self, agent: Agent, dtype=torch.bfloat16):
+        self.agent, self.dtype = agent, dtype
+        dev = agent.actor_logstd.device
+        P = self.PAD
+        self.w0 = torch.zeros((2 * (512 + P), self.IN), dtype=dtype, device=dev)
+        self.b0 = torch.zeros((2 * (512 + P),), dtype=dtype, device=dev)
+        # hidden layers 512 -> 256 -> 128 -> 64 (each + PAD in and out), output layer 64 + PAD -> 8
+        self.w = [torch.zeros((2, o + P, i + P), dtype=dtype, device=dev) for o, i in ((256, 512), (128, 256), (64, 128))]
+        self.w.append(torch.zeros((2, 8, 64 + P), dtype=dtype, device=dev))
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        P = self.PAD
+        nets = (self.agent.actor_mean, self.agent.critic)
+        for k, net in enumerate(nets):
+            base = (512 + P) * k
+            self.w0[base:base + 512, :66].copy_(net[0].weight)
+            self.b0[base:base + 512].copy_(net[0].bias)
+            self.b0[base + 512] = self.ONE                       # the constant-1 channel of the first layer's output
+            for j, layer in enumerate((2, 4, 6, 8)):
+                wgt, bias = net[layer].weight, net[layer].bias
+                o, i = wgt.shape
+                self.w[j][k, :o, :i].copy_(wgt)
+                self.w[j][k, :o, i].copy_(bias)                  # bias column: multiplies the constant-1 channel
+                if j < 3:
+                    self.w[j][k, o, i] = self.ONE                # this layer's own constant-1 channel
+
+    @torch.no_grad()
+    def __call__(self, x72: torch.Tensor):
+        """x72: (rows, 72) normalised observations in `dtype`, columns 66.. zero.  Returns (mean (rows, 3), value (rows, 1)) fp32."""
+        rows = x72.shape[0]
+        h = torch.addmm(self.b0, x72, self.w0.t()).tanh_()           # (rows, 2 * 520) = [actor 512 + 8 | critic 512 + 8]
+        h = h.view(rows, 2, 512 + self.PAD).transpose(0, 1)            # (2, rows, 520), strided: no copy
+        for j in range(3):
+            h = torch.bmm(h, self.w[j].transpose(1, 2)).tanh_()
+        out = torch.bmm(h, self.w[3].transpose(1, 2))                  # (2, rows, 8)
+        return out[0, :, :3].float(), out[1, :, :1].float()
+
+    @torch.no_grad()
+    def act(self, x72: torch.Tensor):
+        """Sampled action, its log-probability and the value (Agent.get_action_and_value with action=None)."""
+        mean, value = self(x72)
+        logstd = self.agent.actor_logstd.float().expand_as(mean)
+        std = logstd.exp()
+        noise = torch.randn_like(mean)
+        action = mean + std * noise
+        logprob = (-0.5 * noise.square() - logstd - 0.9189385332046727).sum(1)  # log N(a; mean, std), a = mean + std z
+        return action, logprob, value
 
 
 def _policy_step(agent, x, policy_dtype):
@@ -163,23 +238,60 @@ class GraphedRollout:
         dev = sim.device
         self.mean32 = torch.zeros((66,), device=dev)
         self.inv_std32 = torch.ones((66,), device=dev)
+        self.shift32 = torch.zeros((66,), device=dev)  # -mean / (std + 1e-8)
         self.next_done = torch.zeros((sim.num_envs, 2), device=dev)
         self.graph = None
+        # bf16 policy: the packed form of the two MLPs and its padded input / fp32 staging buffers
+        self.packed = PackedPolicy(agent, policy_dtype) if policy_dtype is not None else None
+        if self.packed is not None:
+            rows = sim.num_envs * 2
+            self.x32 = torch.empty((rows, 66), device=dev)
+            self.x72 = torch.zeros((rows, PackedPolicy.IN), dtype=policy_dtype, device=dev)
+        # per-step sums and sums of squares of the raw observations, gathered inside the graph; the running statistics merge
+        # them in fp64 after the rollout -- instead of a float64 pass over the whole (T, N, 2, 66) buffer
+        T = buf.obs.shape[0]
+        self.moments = torch.zeros((T, 2, 66), dtype=torch.float64, device=dev)
+        # bf16 policy + bf16 buffer: the three consumers of the observation rows are served by one kernel of the library
+        self.fused_inputs = self.packed is not None and policy_dtype == torch.bfloat16 and buf.obs.dtype == torch.bfloat16
+        self._L = _capi.lib() if self.fused_inputs else None
 
     def _refresh(self):
         self.mean32.copy_(self.normalizer.mean.float())
         self.inv_std32.copy_(1.0 / (self.normalizer.std.float() + 1e-8))
+        self.shift32.copy_(-self.mean32 * self.inv_std32)
+        if self.packed is not None:
+            self.packed.refresh()
 
     @torch.no_grad()
     def _body(self):
         sim, buf, n = self.sim, self.buf, self.sim.num_envs
         full = sim.actions
+        self.moments.zero_()
         for t in range(buf.obs.shape[0]):
             cur = sim.obs[:, :2]  # the blue agents' rows of the simulator's own buffer: no clone
-            buf.obs[t] = cur
             buf.dones[t] = self.next_done
-            x = torch.clamp((cur.reshape(-1, 66) - self.mean32) * self.inv_std32, -10.0, 10.0)
-            action, logprob, value = _policy_step(self.agent, x, self.policy_dtype)
+            if self.fused_inputs:
+                # one pass over the rows (msoc_policy_inputs): normalised + clipped + padded bf16 policy input, the raw
+                # bf16 copy for the buffer, per-feature sum / sum of squares for the running normaliser
+                _capi.check(self._L.msoc_policy_inputs(sim.obs.data_ptr(), n, self.shift32.data_ptr(), self.inv_std32.data_ptr(),
+                                                       self.x72.data_ptr(), buf.obs[t].data_ptr(),
+                                                       self.moments[t].data_ptr() if self.update_normalizer else None,
+                                                       torch.cuda.current_stream(sim.device).cuda_stream))
+            else:
+                buf.obs[t] = cur
+                if self.update_normalizer:  # the step's moments in fp32 (Welford), merged in fp64 after the rollout
+                    v, m = torch.var_mean(cur.reshape(-1, 66), dim=0, unbiased=False)
+                    self.moments[t, 0].copy_(m * (2 * n))
+                    self.moments[t, 1].copy_((v + m.square()) * (2 * n))
+                if self.packed is not None:
+                    torch.addcmul(self.shift32, cur.reshape(-1, 66), self.inv_std32, out=self.x32)
+                    self.x32.clamp_(-10.0, 10.0)
+                    self.x72[:, :66].copy_(self.x32)
+            if self.packed is not None:
+                action, logprob, value = self.packed.act(self.x72)
+            else:
+                x = torch.clamp((cur.reshape(-1, 66) - self.mean32) * self.inv_std32, -10.0, 10.0)
+                action, logprob, value = _policy_step(self.agent, x, self.policy_dtype)
             buf.values[t] = value.reshape(n, 2)
             buf.actions[t] = action.reshape(n, 2, 3)
             buf.logprobs[t] = logprob.reshape(n, 2)
@@ -206,7 +318,10 @@ class GraphedRollout:
         else:
             self.graph.replay()
         if self.update_normalizer:
-            self.normalizer.update(self.buf.obs.reshape(-1, 66))
+            count = self.moments.shape[0] * self.sim.num_envs * 2
+            total = self.moments.sum(0)
+            mean = total[0] / count
+            self.normalizer.update_from_moments(mean, total[1] / count - mean.square(), count)
         return self.sim.obs[:, :2], self.next_done
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from marl_soccer_b200.rollout import Agent, RolloutBuffer, RunningMeanStd, collect_rollout, compute_gae
+from marl_soccer_b200.rollout import Agent, PackedPolicy, RolloutBuffer, RunningMeanStd, collect_rollout, compute_gae
 
 
 def test_agent_architecture_matches_reference_checkpoint_layout():
@@ -27,6 +27,32 @@ def test_agent_architecture_matches_reference_checkpoint_layout():
     ref = torch.distributions.Normal(mean, torch.ones_like(mean)).log_prob(act).sum(1)
     _, logp2, _, _ = a.get_action_and_value(x, act)
     assert torch.allclose(logp2, ref, atol=1e-6)
+
+
+def test_packed_policy_is_the_agent():
+    """PackedPolicy (first layers of both nets as one GEMM over 72-padded inputs, hidden layers batched over the two nets,
+    outputs padded to 8) computes the Agent's means, values and log-probabilities; refresh() follows parameter updates."""
+    torch.manual_seed(3)
+    a = Agent()
+    with torch.no_grad():
+        for p in a.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    pp = PackedPolicy(a, torch.float32)
+    x = torch.randn(41, 66)
+    x72 = torch.zeros(41, PackedPolicy.IN)
+    x72[:, :66] = x
+    mean, value = pp(x72)
+    assert torch.allclose(mean, a.actor_mean(x), atol=1e-5) and torch.allclose(value, a.critic(x), atol=1e-5)
+    action, logprob, value2 = pp.act(x72)
+    _, ref_logprob, _, ref_value = a.get_action_and_value(x, action)
+    assert torch.allclose(logprob, ref_logprob, atol=1e-4) and torch.allclose(value2, ref_value, atol=1e-5)
+    with torch.no_grad():
+        a.actor_mean[0].weight.mul_(2.0)
+        a.actor_logstd.fill_(-0.5)
+    pp.refresh()
+    assert torch.allclose(pp(x72)[0], a.actor_mean(x), atol=1e-5)
+    action, logprob, _ = pp.act(x72)
+    assert torch.allclose(logprob, a.get_action_and_value(x, action)[1], atol=1e-4)
 
 
 def test_running_mean_std_matches_batch_statistics():
@@ -190,3 +216,55 @@ def test_graphed_rollout_runs_the_whole_rollout_as_one_cuda_graph():
     keep = ~sim.done.bool()
     last_blue = buf.obs[T - 1].view(n, 2, 3, 22)
     assert torch.equal(o4[keep][:, :2, 1], last_blue[keep][:, :, 2])
+
+
+@pytest.mark.gpu
+def test_fused_policy_inputs_kernel_and_bf16_graphed_rollout():
+    """msoc_policy_inputs: one pass over the blue agents' observation rows = the normalised, clipped, padded bf16 policy
+    input + the raw bf16 copy + per-feature sums for the running normaliser (marl-soccer.ipynb:385, :403, :264-296);
+    against the same three results computed with torch.  Then the bf16 GraphedRollout that uses it (with the packed
+    policy): its normaliser ends where a float64 pass over the raw observations ends."""
+    import parity_util as P
+    from marl_soccer_b200 import _capi
+    from marl_soccer_b200.rollout import GraphedRollout
+    from marl_soccer_b200.sim import BatchedSoccerSim
+    dev = torch.device("cuda:0")
+    L = _capi.lib()
+    g = torch.Generator(device=dev).manual_seed(2)
+    for n in (1, 5, 1000, 70001):
+        obs = torch.randn((n, 4, 66), generator=g, device=dev) * 3.0
+        obs[0, 0, :4] = torch.tensor([1e4, -1e4, 0.0, 1.0], device=dev)  # clipped at +-10
+        mean, std = torch.randn(66, generator=g, device=dev), torch.rand(66, generator=g, device=dev) + 0.5
+        inv_std = 1.0 / (std + 1e-8)
+        shift = -mean * inv_std
+        x72 = torch.zeros((2 * n, 72), dtype=torch.bfloat16, device=dev)
+        raw = torch.zeros((n, 2, 66), dtype=torch.bfloat16, device=dev)
+        mom = torch.zeros((2, 66), dtype=torch.float64, device=dev)
+        for _ in range(2):  # moments accumulate
+            _capi.check(L.msoc_policy_inputs(obs.data_ptr(), n, shift.data_ptr(), inv_std.data_ptr(), x72.data_ptr(), raw.data_ptr(),
+                                             mom.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        rows = obs[:, :2].reshape(-1, 66)
+        ref = torch.clamp(torch.addcmul(shift, rows, inv_std), -10.0, 10.0).to(torch.bfloat16)
+        assert torch.equal(x72[:, :66], ref) and bool((x72[:, 66:] == 0).all())
+        assert torch.equal(raw, obs[:, :2].to(torch.bfloat16))
+        r64 = rows.to(torch.float64)
+        assert torch.allclose(mom[0], 2 * r64.sum(0), rtol=1e-6, atol=1e-3) and torch.allclose(mom[1], 2 * r64.square().sum(0), rtol=1e-6)
+    # the bf16 rollout on top of it
+    n, T = 4096, 6
+    sim = BatchedSoccerSim(n, config=P.CONFIG, device=dev, seed=3)
+    torch.manual_seed(0)
+    agent = Agent().to(dev)
+    rms, ref_rms = RunningMeanStd((66,), dev), RunningMeanStd((66,), dev)
+    buf = RolloutBuffer(T, n, dev, obs_dtype=torch.bfloat16)
+    sim.reset(2, seed=5)
+    ro = GraphedRollout(sim, agent, rms, buf, policy_dtype=torch.bfloat16)
+    assert ro.fused_inputs
+    for k in range(3):
+        first = sim.obs[:, :2].clone()
+        ro.run()
+        torch.cuda.synchronize()
+        assert torch.equal(buf.obs[0], first.to(torch.bfloat16))
+        ref_rms.update(buf.obs.float())  # the buffer holds the bf16-rounded observations the moments were taken from in fp32
+        assert torch.isfinite(buf.values).all() and torch.isfinite(buf.logprobs).all() and bool((buf.actions.abs() < 20).all())
+    assert torch.allclose(rms.mean, ref_rms.mean, atol=2e-3) and torch.allclose(rms.var, ref_rms.var, rtol=2e-2, atol=1e-3)
+    assert sim.stats()["env_steps"] == 3 * T * n
