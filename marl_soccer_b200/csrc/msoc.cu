@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(FAST_BLOCK, MSOC_FAST_MIN_BLOCKS) msoc_step_fa
     extern __shared__ __align__(16) float s_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * STAGE_WORDS;
+    cudaGridDependencySynchronize(); /* launched programmatically behind the previous kernel of the stream */
     const int step = P.ctl[CTL_STEP_FAST];
     int *ctl = step_ctl(P, step);
     if (blockIdx.x == 0) {
@@ -443,6 +444,7 @@ __device__ __forceinline__ void contact_body(const StepParams &P, int *s_pool_co
     extern __shared__ __align__(16) float s_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float *s_warp = s_dyn + warp * HEAVY_WARP_WORDS;
+    cudaGridDependencySynchronize(); /* launched programmatically behind the streaming kernel: wait until it is complete */
     const int step = P.ctl[CTL_STEP_CONTACT];
     int *ctl = step_ctl(P, step);
     /* this step's fast kernel is complete and the next one starts after this kernel: advance the step counter */
@@ -890,15 +892,31 @@ static int launch_step(msoc_handle *h, StepParams &P, int64_t e0, int64_t e1, in
     P.e0 = e0; P.e1 = e1; P.chunk = chunk;
     const int64_t m = e1 - e0;
     P.heavy_lanes = h->heavy_lanes_override; /* 0: the contact kernel chooses by the number of heavy envs */
-    msoc_step_fast_kernel<<<(unsigned)((m + FAST_BLOCK - 1) / FAST_BLOCK), FAST_BLOCK, FAST_SMEM_BYTES, st>>>(P);
+    /* Both kernels are launched programmatically dependent on whatever kernel precedes them in the stream: their grids
+       are set up while that kernel drains and their blocks wait in cudaGridDependencySynchronize() until it is complete
+       (a few microseconds of launch latency per step, which is what small batches are made of). */
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lf = {};
+    lf.gridDim = dim3((unsigned)((m + FAST_BLOCK - 1) / FAST_BLOCK));
+    lf.blockDim = dim3(FAST_BLOCK);
+    lf.dynamicSmemBytes = FAST_SMEM_BYTES;
+    lf.stream = st;
+    lf.attrs = at; lf.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&lf, msoc_step_fast_kernel, P));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     /* one persistent grid for all contact classes, right behind the streaming kernel */
     const int64_t resident = (int64_t)h->sm_count * h->blocks_per_sm;
     const int64_t blocks_max = (m + HEAVY_BLOCK - 1) / HEAVY_BLOCK;
-    msoc_step_contact_kernel<<<(unsigned)(blocks_max < resident ? blocks_max : resident), HEAVY_BLOCK, STEP_SMEM_BYTES, st>>>(P);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(blocks_max < resident ? blocks_max : resident));
+    lc.blockDim = dim3(HEAVY_BLOCK);
+    lc.dynamicSmemBytes = STEP_SMEM_BYTES;
+    lc.stream = st;
+    lc.attrs = at; lc.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, msoc_step_contact_kernel, P));
     g_launches++;
-    CUDA_TRY(cudaGetLastError());
     return MSOC_OK;
 }
 
