@@ -12,15 +12,15 @@ run() { # N extra-args... -> one line
   fi
 }
 COMMON="--steps 200 --warmup 20 --e2e-steps 5 --no-cpu-baseline --no-extras"
-for n in ${STRONG_N:-1 2 4 8}; do
+for n in ${STRONG_N-1 2 4 8}; do
   run $n $COMMON --global-envs 1048576 2> gpurun_out/${TAG}_strong_${n}gpu.err | tail -1 > gpurun_out/${TAG}_bench_strong_${n}gpu.json
   python -c "import json,sys; d=json.load(open('gpurun_out/${TAG}_bench_strong_${n}gpu.json')); print('strong', d['n_gpus'], '%.4g env-steps/s' % d['value'], '%.4f ms' % d['ms_per_step'], 'e2e %.4g' % d['e2e']['value'], 'envs/gpu', d['config']['envs_per_gpu'])"
 done
-for n in ${WEAK_N:-2 8}; do
+for n in ${WEAK_N-2 8}; do
   run $n $COMMON 2> gpurun_out/${TAG}_weak_${n}gpu.err | tail -1 > gpurun_out/${TAG}_bench_${n}gpu.json
   python -c "import json,sys; d=json.load(open('gpurun_out/${TAG}_bench_${n}gpu.json')); print('weak', d['n_gpus'], '%.4g env-steps/s' % d['value'], '%.4f ms' % d['ms_per_step'], 'e2e %.4g' % d['e2e']['value'], 'full-obs e2e %.4g' % d['e2e']['full_observation']['value'])"
 done
 # what the host <-> device copies alone allow (no kernels): the ceiling of the end-to-end figure
-for n in ${CEIL_N:-1 8}; do
+for n in ${CEIL_N-1 8}; do
   if [ "$n" = 1 ]; then python tools/host_copy_ceiling.py; else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) tools/host_copy_ceiling.py; fi 2>/dev/null | tail -1 | tee gpurun_out/${TAG}_copy_ceiling_${n}gpu.json
 done
