@@ -969,12 +969,16 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
     E.flags = ((uint32_t)mode << FLAG_MODE_SHIFT); /* cache count 0, no bias */
 }
 
-/* One env-step (everything except the observation frames, which the caller builds from E afterwards).
-   MODE_FAST is the contact-free mode used by the kernel's first pass: it returns false -- leaving E
-   meaningless and every array untouched -- as soon as the broad phase finds a candidate pair or the env
-   still carries cached arbiters; such envs are then stepped in full mode (FAST = false, always returns
-   true) on a compacted set of threads.  (A runtime flag, not a template: one copy of the code.)  `load` is the work class of a
-   declined env (0 light, 1 heavy; see below), used to batch envs of similar contact work.  W is only touched when !FAST. */
+/* One env-step (everything except the observation frames, which the caller builds from the stored records afterwards).
+   MODE_FAST is the contact-free mode of the streaming kernel: it returns false -- leaving E meaningless and every array
+   untouched -- as soon as the broad phase finds a candidate pair, and reports the env's work class in `load`; such envs
+   are then stepped by the contact kernel in the mode of their class (always returns true), batched by class:
+     MODE_LIGHT  exactly one candidate pair, agent x segment: narrow phase + solver for one body and <= 2 contacts in registers
+     MODE_PAIR   exactly one candidate pair, agent x agent or ball x agent: one island of two bodies, <= 2 contacts
+     MODE_MULTI  only static candidates, at most two per body: up to five single-body islands, solved one after the other
+     MODE_FULL   anything else: the general Chipmunk path (contact pool, linked arbiter-ordered list, all five bodies)
+   The modes are run-time values under a compile-time mask (ALLOWED): one copy of the prologue and epilogue per kernel.
+   W is only touched by MODE_PAIR / MODE_MULTI (bodies, poses, island slots) and MODE_FULL (everything). */
 enum { MODE_FULL = 0, MODE_FAST = 1, MODE_LIGHT = 2, MODE_PAIR = 3, MODE_MULTI = 4 };
 /* work classes of the envs the contact-free mode declines (`load`): each has its own list and its own code path */
 enum { LOAD_LIGHT = 0, /* exactly one candidate pair, agent x segment: MODE_LIGHT */
@@ -985,9 +989,10 @@ enum { LOAD_LIGHT = 0, /* exactly one candidate pair, agent x segment: MODE_LIGH
 MSOC_HD int mode_of_load(int load) { return load == LOAD_LIGHT ? MODE_LIGHT : load == LOAD_PAIR ? MODE_PAIR : load == LOAD_MULTI ? MODE_MULTI : MODE_FULL; }
 MSOC_HD float sel4(const float *a, int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
-/* Contacts of a register-resident island (MODE_PAIR, MODE_MULTI): the solver fields of a pool record.  The islands of
+/* Contact slots of an island (MODE_PAIR, MODE_MULTI; Work::isl): the solver fields of a pool record.  The islands of
    these modes share no dynamic body with anything else, so solving them on their own, contacts in arbiter order, is the
-   same arithmetic as the general path's sweep over all contacts of the env. */
+   same arithmetic as the general path's sweep over all contacts of the env (bit-identical on the host build:
+   tests/test_hostsim_parity.py). */
 enum { IF_NX, IF_NY, IF_RN1, IF_RT1, IF_RN2, IF_RT2, IF_NM, IF_TM, IF_BIAS, IF_BNC, IF_JN, IF_JT, IF_JB, IF_INFO, ISL_FIELDS };
 enum { IF_U = IF_RN1 }; /* a static x body contact has no first arm: its slot carries the friction coefficient there */
 constexpr int ISL_SLOTS = 4;
