@@ -226,7 +226,7 @@ def collect_rollout(sim, agent: Agent, normalizer: RunningMeanStd, buf: RolloutB
 
 class GraphedRollout:
     """collect_rollout as ONE CUDA graph per rollout: the T steps (normalise -> MLPs -> sample -> red actions ->
-    msoc_step's three kernels -> storage) are captured once and replayed, so the ~40 launches per step cost no host
+    msoc_step's two kernels -> storage) are captured once and replayed, so the ~30 launches per step cost no host
     time and the simulator is never waiting for Python.  The simulator's step counter lives in device memory, which
     is what makes a captured sequence of steps replayable (include/msoc.h).  Sampling uses torch's default CUDA
     generator (graph-safe)."""
