@@ -14,9 +14,16 @@ from . import _capi
 
 
 class HostBufferSim:
-    def __init__(self, n: int, config: dict, seed: int = 0, global_offset: int = 0, device: int = 0):
+    """pinned=True keeps ONE set of page-locked host buffers for the lifetime of the sim (allocated through torch) and
+    returns views of them: the copies then run at PCIe speed instead of through the driver's bounce buffers (what bench.py
+    measures as `e2e`), but the arrays a step returns are overwritten by the next step -- copy what you keep.  The default
+    (fresh pageable arrays every call) has the reference's value semantics."""
+
+    def __init__(self, n: int, config: dict, seed: int = 0, global_offset: int = 0, device: int = 0, pinned: bool = False):
         self._L = _capi.lib()
         self.n = int(n)
+        self._pin = {}
+        self._pinned = bool(pinned)
         self.config = config
         self._cfg = _capi.make_config(config)
         h = C.c_void_p()
@@ -32,8 +39,26 @@ class HostBufferSim:
 
     __del__ = close
 
+    def _out(self, name: str, shape, dtype) -> np.ndarray:
+        """Output array: fresh and pageable, or the sim's persistent page-locked one."""
+        if not self._pinned:
+            return np.zeros(shape, dtype)
+        if name not in self._pin:
+            import torch
+            t = torch.zeros(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+            self._pin[name] = (t, t.numpy())  # the tensor owns the page-locked allocation
+        return self._pin[name][1]
+
+    def _in(self, actions) -> np.ndarray:
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 12)
+        if self._pinned:
+            buf = self._out("actions", (self.n, 12), np.float32)
+            np.copyto(buf, a)
+            return buf
+        return a
+
     def reset(self, mode: int = _capi.MODE_RANDOM, seed: int | None = None, mask=None) -> np.ndarray:
-        obs = np.zeros((self.n, 4, 66), np.float32)
+        obs = self._out("obs", (self.n, 4, 66), np.float32)
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         _capi.check(self._L.msoc_reset_host(self._h, None if m is None else m.ctypes.data, int(mode),
                                             0 if seed is None else 1,
@@ -41,12 +66,12 @@ class HostBufferSim:
         return obs
 
     def step(self, actions, auto_reset: bool = True):
-        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 12)
-        obs = np.zeros((self.n, 4, 66), np.float32)
-        rew = np.zeros((self.n, 2), np.float32)
-        done = np.zeros(self.n, np.uint8)
-        goal = np.zeros(self.n, np.int8)
-        self.score = np.zeros((self.n, 2), np.int32)
+        a = self._in(actions)
+        obs = self._out("obs", (self.n, 4, 66), np.float32)
+        rew = self._out("rew", (self.n, 2), np.float32)
+        done = self._out("done", (self.n,), np.uint8)
+        goal = self._out("goal", (self.n,), np.int8)
+        self.score = self._out("score", (self.n, 2), np.int32)
         _capi.check(self._L.msoc_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
                                            done.ctypes.data, goal.ctypes.data, self.score.ctypes.data,
                                            _capi.STEP_AUTO_RESET if auto_reset else 0, None))
@@ -56,12 +81,12 @@ class HostBufferSim:
         """msoc_step_host_frames: like step(), but only the newest 22-float frame of every agent comes back, (N,4,22) --
         a third of the D2H bytes.  The caller owns the 3-frame stack: append the frame; where `done` is set (and
         auto_reset) the frame is the first one of the next episode and fills all three slots."""
-        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.n, 12)
-        frames = np.zeros((self.n, 4, 22), np.float32)
-        rew = np.zeros((self.n, 2), np.float32)
-        done = np.zeros(self.n, np.uint8)
-        goal = np.zeros(self.n, np.int8)
-        self.score = np.zeros((self.n, 2), np.int32)
+        a = self._in(actions)
+        frames = self._out("frames", (self.n, 4, 22), np.float32)
+        rew = self._out("rew", (self.n, 2), np.float32)
+        done = self._out("done", (self.n,), np.uint8)
+        goal = self._out("goal", (self.n,), np.int8)
+        self.score = self._out("score", (self.n, 2), np.int32)
         _capi.check(self._L.msoc_step_host_frames(self._h, a.ctypes.data, frames.ctypes.data, rew.ctypes.data,
                                                   done.ctypes.data, goal.ctypes.data, self.score.ctypes.data,
                                                   _capi.STEP_AUTO_RESET if auto_reset else 0, None))

@@ -66,10 +66,12 @@ class _EnvView:
 
 class SyncMultiAgentVecEnv:
     def __init__(self, env_fns, *, num_envs: Optional[int] = None, config: Optional[dict] = None, seed: Optional[int] = None,
-                 device: int = 0, global_env_offset: int = 0, _sim_factory=None):
+                 device: int = 0, global_env_offset: int = 0, pinned_buffers: bool = False, _sim_factory=None):
         """env_fns: list of callables as in the reference; only its length and (when `config` is not given)
         the config of env_fns[0]() are used -- N single-env CUDA handles would defeat the batching.
-        Alternatively pass env_fns=None with num_envs / config."""
+        Alternatively pass env_fns=None with num_envs / config.  pinned_buffers: one persistent set of page-locked host
+        buffers (HostBufferSim(pinned=True)): full PCIe speed for large batches, but the arrays step() returns are then
+        views that the next step overwrites."""
         if env_fns is not None:
             n = len(env_fns)
             if config is None:
@@ -91,7 +93,7 @@ class SyncMultiAgentVecEnv:
             seed = int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0] >> 1)
         if _sim_factory is None:
             from .host_api import HostBufferSim
-            self._sim = HostBufferSim(n, config, seed=seed, global_offset=global_env_offset, device=device)
+            self._sim = HostBufferSim(n, config, seed=seed, global_offset=global_env_offset, device=device, pinned=pinned_buffers)
         else:
             self._sim = _sim_factory(n, config, seed)
         self.envs = [_EnvView(self, i) for i in range(n)]

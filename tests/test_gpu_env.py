@@ -121,6 +121,31 @@ def test_torch_vec_env_equals_numpy_vec_env():
     tv.close(); nv.close()
 
 
+def test_vec_env_with_persistent_pinned_buffers():
+    """SyncMultiAgentVecEnv(pinned_buffers=True): one set of page-locked host buffers for the lifetime of the env, step()
+    returns views of them -- the same numbers as the default (fresh arrays), and the previous step's arrays are reused."""
+    n = 257
+    cfg = {**P.CONFIG, "simulation": {"max_steps": 5}}
+    a_env = marl_vecenv.SyncMultiAgentVecEnv(None, num_envs=n, config=cfg, seed=4)
+    b_env = marl_vecenv.SyncMultiAgentVecEnv(None, num_envs=n, config=cfg, seed=4, pinned_buffers=True)
+    oa = a_env.reset(seed=9, options={"use_full_random_positions": True})
+    ob = b_env.reset(seed=9, options={"use_full_random_positions": True})
+    assert np.array_equal(oa, ob)
+    rng = np.random.default_rng(1)
+    first = None
+    for t in range(11):
+        act = rng.uniform(-1, 1, (n, 4, 3)).astype(np.float32)
+        ra, rb = a_env.step(act), b_env.step(act)
+        for x, y in zip(ra[:4], rb[:4]):
+            assert np.array_equal(x, y)
+        assert ra[4][0] == rb[4][0] and ra[4][n - 1] == rb[4][n - 1]
+        if first is None:
+            first = rb[0]
+        else:
+            assert np.shares_memory(first, rb[0])  # the same page-locked buffer every step
+    a_env.close(); b_env.close()
+
+
 def test_make_sharded_sim_single_process():
     """distributed.make_sharded_sim without a process group is the whole range on this GPU (rank 0 of 1), and two
     explicit shards with global offsets reproduce it (marl_vecenv.py:39-42: envs never interact)."""

@@ -157,7 +157,7 @@ def test_chunked_host_step_equals_the_whole_step():
     n = 200_000  # three chunks
     cfg = {**P.CONFIG, "simulation": {"max_steps": 9}}
     host = HostBufferSim(n, cfg, seed=5)
-    fr = HostBufferSim(n, cfg, seed=5)
+    fr = HostBufferSim(n, cfg, seed=5, pinned=True)  # persistent page-locked buffers: views, overwritten by the next step
     dev = BatchedSoccerSim(n, config=cfg, seed=5)
     a = host.reset(O.MODE_FULL_RANDOM, seed=2)
     fr.reset(O.MODE_FULL_RANDOM, seed=2)
