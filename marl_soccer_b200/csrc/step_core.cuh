@@ -974,7 +974,8 @@ MSOC_HD void env_full_reset(Env &E, int mode, uint64_t seed, uint64_t gidx, uint
    untouched -- as soon as the broad phase finds a candidate pair, and reports the env's work class in `load`; such envs
    are then stepped by the contact kernel in the mode of their class (always returns true), batched by class:
      MODE_LIGHT  exactly one candidate pair, agent x segment: narrow phase + solver for one body and <= 2 contacts in registers
-     MODE_PAIR   exactly one candidate pair, agent x agent or ball x agent: one island of two bodies, <= 2 contacts
+     MODE_PAIR   exactly one agent x agent / ball x agent candidate pair (+ at most one agent x segment pair): one island of
+                 two bodies and <= 4 contacts, or that island and a single-body one
      MODE_MULTI  only static candidates, at most two per body: up to five single-body islands, solved one after the other
      MODE_FULL   anything else: the general Chipmunk path (contact pool, linked arbiter-ordered list, all five bodies)
    The modes are run-time values under a compile-time mask (ALLOWED): one copy of the prologue and epilogue per kernel.
@@ -983,7 +984,7 @@ enum { MODE_FULL = 0, MODE_FAST = 1, MODE_LIGHT = 2, MODE_PAIR = 3, MODE_MULTI =
 /* work classes of the envs the contact-free mode declines (`load`): each has its own list and its own code path */
 enum { LOAD_LIGHT = 0, /* exactly one candidate pair, agent x segment: MODE_LIGHT */
        LOAD_HEAVY = 1, /* anything else: the general Chipmunk path, MODE_FULL */
-       LOAD_PAIR = 2,  /* exactly one candidate pair, agent x agent or ball x agent: MODE_PAIR */
+       LOAD_PAIR = 2,  /* exactly one agent x agent or ball x agent candidate pair, at most one agent x segment pair beside it: MODE_PAIR */
        LOAD_MULTI = 3, /* only static candidates (agent x segment, ball x wall), at most two per body: MODE_MULTI */
        N_LOADS = 4 };
 MSOC_HD int mode_of_load(int load) { return load == LOAD_LIGHT ? MODE_LIGHT : load == LOAD_PAIR ? MODE_PAIR : load == LOAD_MULTI ? MODE_MULTI : MODE_FULL; }
@@ -1138,7 +1139,7 @@ MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *ac
                     for (int i = 0; i < 4; i++) ok = ok && popc32((m_as >> (8 * i)) & 255u) <= 2;
                     load = ok ? LOAD_MULTI : LOAD_HEAVY;
                 }
-            } else load = (n_dyn == 1 && n_as == 0 && n_bw == 0) ? LOAD_PAIR : LOAD_HEAVY;
+            } else load = (n_dyn == 1 && n_as <= 1 && n_bw == 0) ? LOAD_PAIR : LOAD_HEAVY;
             return false;
         }
         /* an injected state (Arrays::inject): the general kernel steps it (rare: only the step after msoc_set_state) */
@@ -1370,118 +1371,40 @@ MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *ac
             for (int j = 4; j < old_count; j++) one(oc[3 * j], oc[3 * j + 1], oc[3 * j + 2]);
         };
 
+        /* ---- pair class: exactly one candidate pair that joins two dynamic bodies -- agent i x agent j (a = i, b = j) or
+           ball x agent (a = ball, b = agent), at most two contacts -- and at most one agent x segment candidate beside it.
+           The wall arbiter comes first in arbiter order.  If its agent is one of the pair's bodies and both manifolds have
+           contacts, the four contacts are ONE island of two bodies (slots 0-1 wall, 2-3 pair); otherwise the wall agent is a
+           single-body island of its own and goes through the multi class's loop below. */
+        bool aa = false, wall_merged = false;
+        int ia_ = 0, ib_ = 1, pair = 0, wl_idx = 0;
+        Manifold m;
+        m.count = 0;
+        V2 r1_off = mk(0.0f, 0.0f), r2_off = mk(0.0f, 0.0f);
+        uint32_t loop_as = run_multi ? m_as : 0u, loop_bw = run_multi ? m_bw : 0u; /* candidates of the single-body loop */
         if (run_pair) {
-            /* ---- exactly one candidate pair and it joins two dynamic bodies: agent i x agent j (a = i, b = j) or
-               ball x agent (a = ball, b = agent); at most two contacts */
-            const bool aa = m_aa != 0u;
+            aa = m_aa != 0u;
             const int idx = aa ? ctz32(m_aa) : ctz32(m_ba);
-            const int ia_ = aa ? ((idx < 3) ? 0 : (idx < 5) ? 1 : 2) : BALL;
-            const int ib_ = aa ? ((idx < 3) ? idx + 1 : (idx < 5) ? idx - 1 : 3) : idx;
-            const int pair = (aa ? PAIR_AGENT_AGENT : PAIR_BALL_AGENT) + idx;
-            float *pa = W.body + ia_ * SCR, *pb = W.body + ib_ * SCR;
+            ia_ = aa ? ((idx < 3) ? 0 : (idx < 5) ? 1 : 2) : BALL;
+            ib_ = aa ? ((idx < 3) ? idx + 1 : (idx < 5) ? idx - 1 : 3) : idx;
+            pair = (aa ? PAIR_AGENT_AGENT : PAIR_BALL_AGENT) + idx;
             const V2 off = mk(G[(GF_PX + ib_) * SCR] - G[(GF_PX + ia_) * SCR], G[(GF_PY + ib_) * SCR] - G[(GF_PY + ia_) * SCR]); /* centre b - centre a */
-            Manifold m;
-            V2 r1_off = mk(0.0f, 0.0f), r2_off = mk(0.0f, 0.0f);
             if (aa) { collide_box_box(G[(GF_CS + (ia_ & 3)) * SCR], G[(GF_SN + (ia_ & 3)) * SCR], G[(GF_CS + ib_) * SCR], G[(GF_SN + ib_) * SCR], off, m); r2_off = off; }
             else { const V2 cb = vneg(off); collide_ball_box(cb, G[(GF_CS + ib_) * SCR], G[(GF_SN + ib_) * SCR], m); r1_off = cb; }
-            n_contacts = m.count;
-            if (m.count > 0) {
-                const bool two = m.count > 1;
-                touched |= 1ull << pair;
-                solved |= (1u << ia_) | (1u << ib_);
-                cache_lookup(pair, m.key[0], two ? m.key[1] : -1);
-                const float ma = aa ? c.agent_minv : c.ball_minv, iam = aa ? c.agent_iinv : c.ball_iinv;
-                const float mb = c.agent_minv, ibm = c.agent_iinv;
-                const float e_ = aa ? E_AGENT_AGENT : E_BALL_AGENT, u = aa ? U_AGENT_AGENT : U_BALL_AGENT;
-                const float nx = m.n.x, ny = m.n.y;
-                const V2 tng = vperp(m.n);
-                /* pre-update velocities: parked in the bias fields */
-                const float oax = pa[BF_BX * BODY_FS], oay = pa[BF_BY * BODY_FS], oaw = pa[BF_BW * BODY_FS];
-                const float obx = pb[BF_BX * BODY_FS], oby = pb[BF_BY * BODY_FS], obw = pb[BF_BW * BODY_FS];
-#pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    if (i == 0 || two) {
-                        float *q = W.isl + i * ISL_FIELDS * SCR;
-                        const V2 r1 = m.p1[i] - r1_off, r2 = m.p2[i] - r2_off;
-                        const float rn1 = vcross(r1, m.n), rt1 = vcross(r1, tng), rn2 = vcross(r2, m.n), rt2 = vcross(r2, tng);
-                        q[IF_RN1 * SCR] = rn1; q[IF_RT1 * SCR] = rt1; q[IF_RN2 * SCR] = rn2; q[IF_RT2 * SCR] = rt2;
-                        q[IF_NM * SCR] = 1.0f / (ma + iam * rn1 * rn1 + mb + ibm * rn2 * rn2);
-                        q[IF_TM * SCR] = 1.0f / (ma + iam * rt1 * rt1 + mb + ibm * rt2 * rt2);
-                        q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[i] - m.p1[i], m.n) + SLOP);
-                        float vn = 0.0f;
-                        vn -= oax * nx + oay * ny + oaw * rn1;
-                        vn += obx * nx + oby * ny + obw * rn2;
-                        q[IF_BNC * SCR] = vn * e_;
-                        q[IF_JN * SCR] = (i == 0) ? cjn0 : cjn1; q[IF_JT * SCR] = (i == 0) ? cjt0 : cjt1; q[IF_JB * SCR] = 0.0f;
-                    }
-                }
-                float avx = pa[BF_VX * BODY_FS], avy = pa[BF_VY * BODY_FS], aw = pa[BF_W * BODY_FS], abx = 0.0f, aby = 0.0f, abw = 0.0f;
-                float bvx = pb[BF_VX * BODY_FS], bvy = pb[BF_VY * BODY_FS], bw_ = pb[BF_W * BODY_FS], bbx = 0.0f, bby = 0.0f, bbw = 0.0f;
-                /* cpArbiterApplyCachedImpulse (skipped in an arbiter's first step) */
-                if (!first) {
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        if (i == 0 || two) {
-                            const float *q = W.isl + i * ISL_FIELDS * SCR;
-                            const float jn = q[IF_JN * SCR], jt = q[IF_JT * SCR];
-                            const float jx = nx * jn - ny * jt, jy = ny * jn + nx * jt;
-                            avx -= jx * ma; avy -= jy * ma; aw -= iam * (q[IF_RN1 * SCR] * jn + q[IF_RT1 * SCR] * jt);
-                            bvx += jx * mb; bvy += jy * mb; bw_ += ibm * (q[IF_RN2 * SCR] * jn + q[IF_RT2 * SCR] * jt);
-                        }
-                    }
-                }
-                /* cpArbiterApplyImpulse x 10 */
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-                for (int it = 0; it < SOLVER_ITERS; it++) {
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        if (i == 0 || two) {
-                            float *q = W.isl + i * ISL_FIELDS * SCR;
-                            const float rn1 = q[IF_RN1 * SCR], rt1 = q[IF_RT1 * SCR], rn2 = q[IF_RN2 * SCR], rt2 = q[IF_RT2 * SCR];
-                            const float nM = q[IF_NM * SCR], jbO = q[IF_JB * SCR], jnO = q[IF_JN * SCR], jtO = q[IF_JT * SCR];
-                            float vrn = bvx * nx + bvy * ny + bw_ * rn2;
-                            float vrt = bvy * nx - bvx * ny + bw_ * rt2;
-                            float vbn = bbx * nx + bby * ny + bbw * rn2;
-                            vrn -= avx * nx + avy * ny + aw * rn1;
-                            vrt -= avy * nx - avx * ny + aw * rt1;
-                            vbn -= abx * nx + aby * ny + abw * rn1;
-                            const float jbN = fmaxf(jbO + (q[IF_BIAS * SCR] - vbn) * nM, 0.0f);
-                            const float jnN = fmaxf(jnO - (q[IF_BNC * SCR] + vrn) * nM, 0.0f);
-                            const float jtMax = u * jnN;
-                            const float jtN = fminf(fmaxf(jtO - vrt * q[IF_TM * SCR], -jtMax), jtMax);
-                            const float djb = jbN - jbO, djn = jnN - jnO, djt = jtN - jtO;
-                            q[IF_JB * SCR] = jbN; q[IF_JN * SCR] = jnN; q[IF_JT * SCR] = jtN;
-                            const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
-                            bbx += nx * djb * mb; bby += ny * djb * mb; bbw += ibm * rn2 * djb;
-                            bvx += jx * mb; bvy += jy * mb; bw_ += ibm * (rn2 * djn + rt2 * djt);
-                            abx -= nx * djb * ma; aby -= ny * djb * ma; abw -= iam * rn1 * djb;
-                            avx -= jx * ma; avy -= jy * ma; aw -= iam * (rn1 * djn + rt1 * djt);
-                        }
-                    }
-                }
-                pa[BF_VX * BODY_FS] = avx; pa[BF_VY * BODY_FS] = avy; pa[BF_W * BODY_FS] = aw;
-                pa[BF_BX * BODY_FS] = abx; pa[BF_BY * BODY_FS] = aby; pa[BF_BW * BODY_FS] = abw;
-                pb[BF_VX * BODY_FS] = bvx; pb[BF_VY * BODY_FS] = bvy; pb[BF_W * BODY_FS] = bw_;
-                pb[BF_BX * BODY_FS] = bbx; pb[BF_BY * BODY_FS] = bby; pb[BF_BW * BODY_FS] = bbw;
-                /* this step's contacts open the arbiter cache of the next step (age 0) */
-                nc_[0] = (uint32_t)pair | ((uint32_t)m.key[0] << 6); nc_[1] = f2u(W.isl[IF_JN * SCR]); nc_[2] = f2u(W.isl[IF_JT * SCR]);
-                new_count = 1;
-                if (two) {
-                    const float *q = W.isl + ISL_FIELDS * SCR;
-                    nc_[3] = (uint32_t)pair | ((uint32_t)m.key[1] << 6); nc_[4] = f2u(q[IF_JN * SCR]); nc_[5] = f2u(q[IF_JT * SCR]);
-                    new_count = 2;
-                }
+            if (m_as != 0u) {
+                wl_idx = ctz32(m_as);
+                const int wa = wl_idx >> 3;
+                wall_merged = m.count > 0 && (wa == ia_ || wa == ib_);
+                if (!wall_merged) loop_as = m_as;
             }
         }
 
-        if (run_multi) {
-            /* ---- only static candidates: every touched body is an island of its own -- one dynamic body against the
-               static one, at most two arbiters (four contacts) -- solved one after the other, bodies and arbiters in
-               ascending order (the canonical arbiter order restricted to this env) */
-            uint32_t bodies = ((m_as & 0xffu) ? 1u : 0u) | ((m_as & 0xff00u) ? 2u : 0u) | ((m_as & 0xff0000u) ? 4u : 0u) |
-                              ((m_as & 0xff000000u) ? 8u : 0u) | (m_bw ? 16u : 0u);
+        if ((loop_as | loop_bw) != 0u) {
+            /* ---- single-body islands -- one dynamic body against the static one, at most two arbiters (four contacts) --
+               solved one after the other, bodies and arbiters in ascending order (the canonical arbiter order restricted
+               to them): all of a multi env, the separate wall agent of a pair env */
+            uint32_t bodies = ((loop_as & 0xffu) ? 1u : 0u) | ((loop_as & 0xff00u) ? 2u : 0u) | ((loop_as & 0xff0000u) ? 4u : 0u) |
+                              ((loop_as & 0xff000000u) ? 8u : 0u) | (loop_bw ? 16u : 0u);
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -1489,7 +1412,7 @@ MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *ac
                 const int b = ctz32(bodies);
                 bodies &= bodies - 1u;
                 const bool ag = b < 4;
-                uint32_t segs = ag ? ((m_as >> (8 * b)) & 255u) : m_bw;
+                uint32_t segs = ag ? ((loop_as >> (8 * b)) & 255u) : loop_bw;
                 float *pb = W.body + b * SCR;
                 const V2 pos = mk(G[(GF_PX + b) * SCR], G[(GF_PY + b) * SCR]);
                 const float bcs = G[(GF_CS + (b & 3)) * SCR], bsn = G[(GF_SN + (b & 3)) * SCR];
@@ -1505,30 +1428,30 @@ MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *ac
                     const int sg = ctz32(segs);
                     segs &= segs - 1u;
                     const Seg g = get_segment(sg);
-                    Manifold m;
-                    if (ag) collide_segment_box(g, pos, bcs, bsn, m);
-                    else collide_ball_segment(g, pos, m);
-                    if (m.count == 0) continue;
-                    const int pair = ag ? 8 * b + sg : PAIR_BALL_WALL + sg;
-                    const bool two = m.count > 1;
-                    touched |= 1ull << pair;
-                    cache_lookup(pair, m.key[0], two ? m.key[1] : -1);
+                    Manifold mw;
+                    if (ag) collide_segment_box(g, pos, bcs, bsn, mw);
+                    else collide_ball_segment(g, pos, mw);
+                    if (mw.count == 0) continue;
+                    const int wpair = ag ? 8 * b + sg : PAIR_BALL_WALL + sg;
+                    const bool two = mw.count > 1;
+                    touched |= 1ull << wpair;
+                    cache_lookup(wpair, mw.key[0], two ? mw.key[1] : -1);
                     /* stored with the dynamic body second (add_contacts): a ball x wall manifold (ball first) is flipped */
-                    const V2 n_ = ag ? m.n : vneg(m.n), tng = vperp(n_);
+                    const V2 n_ = ag ? mw.n : vneg(mw.n), tng = vperp(n_);
                     const float u_ = ag ? ((sg < 6) ? U_AGENT_WALL : U_AGENT_GOALLINE) : U_BALL_WALL;
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
                         if ((i == 0 || two) && cnt < ISL_SLOTS) {
                             float *q = W.isl + cnt * ISL_FIELDS * SCR;
-                            const V2 r2 = ag ? m.p2[i] : m.p1[i];
+                            const V2 r2 = ag ? mw.p2[i] : mw.p1[i];
                             const float rn = vcross(r2, n_), rt = vcross(r2, tng);
                             q[IF_NX * SCR] = n_.x; q[IF_NY * SCR] = n_.y; q[IF_RN2 * SCR] = rn; q[IF_RT2 * SCR] = rt;
                             q[IF_NM * SCR] = 1.0f / (mb + ibm * rn * rn); q[IF_TM * SCR] = 1.0f / (mb + ibm * rt * rt);
-                            q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[i] - m.p1[i], m.n) + SLOP);
+                            q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(mw.p2[i] - mw.p1[i], mw.n) + SLOP);
                             q[IF_BNC * SCR] = (obx * n_.x + oby * n_.y + obw * rn) * e_;
                             q[IF_JN * SCR] = (i == 0) ? cjn0 : cjn1; q[IF_JT * SCR] = (i == 0) ? cjt0 : cjt1; q[IF_JB * SCR] = 0.0f;
                             q[IF_U * SCR] = u_;
-                            q[IF_INFO * SCR] = u2f((uint32_t)pair | ((uint32_t)m.key[i] << 6));
+                            q[IF_INFO * SCR] = u2f((uint32_t)wpair | ((uint32_t)mw.key[i] << 6));
                             if (first) firsts |= 1u << cnt;
                             cnt++;
                         }
@@ -1581,6 +1504,175 @@ MSOC_HD bool env_step(const int MODE, const int ALLOWED, Env &E, const float *ac
                 }
                 n_contacts += cnt;
             }
+        }
+
+        if (run_pair && m.count > 0) {
+            /* ---- the pair's island: two bodies in registers; slots 2-3 its own (<= 2) contacts, slots 0-1 the (<= 2)
+               contacts of the wall arbiter of one of its agents when there is one (wall_merged) */
+            const bool two = m.count > 1;
+            float *pa = W.body + ia_ * SCR, *pb = W.body + ib_ * SCR;
+            const float ma = aa ? c.agent_minv : c.ball_minv, iam = aa ? c.agent_iinv : c.ball_iinv;
+            const float mb = c.agent_minv, ibm = c.agent_iinv;
+            /* pre-update velocities: parked in the bias fields */
+            const float oax = pa[BF_BX * BODY_FS], oay = pa[BF_BY * BODY_FS], oaw = pa[BF_BW * BODY_FS];
+            const float obx = pb[BF_BX * BODY_FS], oby = pb[BF_BY * BODY_FS], obw = pb[BF_BW * BODY_FS];
+            /* the wall arbiter first (arbiter order) */
+            int wcnt = 0;
+            bool wfirst = true, wall_on_a = false;
+            if (wall_merged) {
+                const int wa = wl_idx >> 3, sg = wl_idx & 7;
+                wall_on_a = wa == ia_;
+                const Seg g = get_segment(sg);
+                Manifold mw;
+                collide_segment_box(g, mk(G[(GF_PX + wa) * SCR], G[(GF_PY + wa) * SCR]), G[(GF_CS + wa) * SCR], G[(GF_SN + wa) * SCR], mw);
+                if (mw.count > 0) {
+                    const bool wtwo = mw.count > 1;
+                    touched |= 1ull << wl_idx;
+                    cache_lookup(wl_idx, mw.key[0], wtwo ? mw.key[1] : -1);
+                    wfirst = first;
+                    const V2 tng = vperp(mw.n);
+                    const float ovx_ = wall_on_a ? oax : obx, ovy_ = wall_on_a ? oay : oby, ow_ = wall_on_a ? oaw : obw;
+                    const float u_ = (sg < 6) ? U_AGENT_WALL : U_AGENT_GOALLINE;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        if (i == 0 || wtwo) {
+                            float *q = W.isl + i * ISL_FIELDS * SCR;
+                            const float rn = vcross(mw.p2[i], mw.n), rt = vcross(mw.p2[i], tng);
+                            q[IF_NX * SCR] = mw.n.x; q[IF_NY * SCR] = mw.n.y; q[IF_RN2 * SCR] = rn; q[IF_RT2 * SCR] = rt;
+                            q[IF_NM * SCR] = 1.0f / (c.agent_minv + c.agent_iinv * rn * rn); q[IF_TM * SCR] = 1.0f / (c.agent_minv + c.agent_iinv * rt * rt);
+                            q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(mw.p2[i] - mw.p1[i], mw.n) + SLOP);
+                            q[IF_BNC * SCR] = (ovx_ * mw.n.x + ovy_ * mw.n.y + ow_ * rn) * E_AGENT_SEG;
+                            q[IF_JN * SCR] = (i == 0) ? cjn0 : cjn1; q[IF_JT * SCR] = (i == 0) ? cjt0 : cjt1; q[IF_JB * SCR] = 0.0f;
+                            q[IF_U * SCR] = u_;
+                            q[IF_INFO * SCR] = u2f((uint32_t)wl_idx | ((uint32_t)mw.key[i] << 6));
+                        }
+                    }
+                    wcnt = mw.count;
+                }
+            }
+            touched |= 1ull << pair;
+            solved |= (1u << ia_) | (1u << ib_);
+            cache_lookup(pair, m.key[0], two ? m.key[1] : -1);
+            const float e_ = aa ? E_AGENT_AGENT : E_BALL_AGENT, u = aa ? U_AGENT_AGENT : U_BALL_AGENT;
+            const float nx = m.n.x, ny = m.n.y;
+            const V2 tng = vperp(m.n);
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (i == 0 || two) {
+                    float *q = W.isl + (2 + i) * ISL_FIELDS * SCR;
+                    const V2 r1 = m.p1[i] - r1_off, r2 = m.p2[i] - r2_off;
+                    const float rn1 = vcross(r1, m.n), rt1 = vcross(r1, tng), rn2 = vcross(r2, m.n), rt2 = vcross(r2, tng);
+                    q[IF_RN1 * SCR] = rn1; q[IF_RT1 * SCR] = rt1; q[IF_RN2 * SCR] = rn2; q[IF_RT2 * SCR] = rt2;
+                    q[IF_NM * SCR] = 1.0f / (ma + iam * rn1 * rn1 + mb + ibm * rn2 * rn2);
+                    q[IF_TM * SCR] = 1.0f / (ma + iam * rt1 * rt1 + mb + ibm * rt2 * rt2);
+                    q[IF_BIAS * SCR] = -BIAS_COEF_OVER_DT * fminf(0.0f, vdot(m.p2[i] - m.p1[i], m.n) + SLOP);
+                    float vn = 0.0f;
+                    vn -= oax * nx + oay * ny + oaw * rn1;
+                    vn += obx * nx + oby * ny + obw * rn2;
+                    q[IF_BNC * SCR] = vn * e_;
+                    q[IF_JN * SCR] = (i == 0) ? cjn0 : cjn1; q[IF_JT * SCR] = (i == 0) ? cjt0 : cjt1; q[IF_JB * SCR] = 0.0f;
+                }
+            }
+            float avx = pa[BF_VX * BODY_FS], avy = pa[BF_VY * BODY_FS], aw = pa[BF_W * BODY_FS], abx = 0.0f, aby = 0.0f, abw = 0.0f;
+            float bvx = pb[BF_VX * BODY_FS], bvy = pb[BF_VY * BODY_FS], bw_ = pb[BF_W * BODY_FS], bbx = 0.0f, bby = 0.0f, bbw = 0.0f;
+            /* one contact of the wall arbiter against the agent it belongs to (warm = cpArbiterApplyCachedImpulse, else
+               cpArbiterApplyImpulse), the same arithmetic as in the single-body loop above */
+            auto wall_contact = [&](int k, bool warm, float &vx, float &vy, float &w, float &bx, float &by, float &bw) {
+                float *q = W.isl + k * ISL_FIELDS * SCR;
+                const float wnx = q[IF_NX * SCR], wny = q[IF_NY * SCR], rn = q[IF_RN2 * SCR], rt = q[IF_RT2 * SCR];
+                const float jbO = q[IF_JB * SCR], jnO = q[IF_JN * SCR], jtO = q[IF_JT * SCR];
+                if (warm) {
+                    const float jx = wnx * jnO - wny * jtO, jy = wny * jnO + wnx * jtO;
+                    vx += jx * c.agent_minv; vy += jy * c.agent_minv; w += c.agent_iinv * (rn * jnO + rt * jtO);
+                    return;
+                }
+                const float nM = q[IF_NM * SCR];
+                const float vrn = vx * wnx + vy * wny + w * rn;
+                const float vrt = vy * wnx - vx * wny + w * rt;
+                const float vbn = bx * wnx + by * wny + bw * rn;
+                const float jbN = fmaxf(jbO + (q[IF_BIAS * SCR] - vbn) * nM, 0.0f);
+                const float jnN = fmaxf(jnO - (q[IF_BNC * SCR] + vrn) * nM, 0.0f);
+                const float jtMax = q[IF_U * SCR] * jnN;
+                const float jtN = fminf(fmaxf(jtO - vrt * q[IF_TM * SCR], -jtMax), jtMax);
+                const float djb = jbN - jbO, djn = jnN - jnO, djt = jtN - jtO;
+                q[IF_JB * SCR] = jbN; q[IF_JN * SCR] = jnN; q[IF_JT * SCR] = jtN;
+                const float jx = wnx * djn - wny * djt, jy = wny * djn + wnx * djt;
+                bx += wnx * djb * c.agent_minv; by += wny * djb * c.agent_minv; bw += c.agent_iinv * rn * djb;
+                vx += jx * c.agent_minv; vy += jy * c.agent_minv; w += c.agent_iinv * (rn * djn + rt * djt);
+            };
+            /* cpArbiterApplyCachedImpulse (skipped in an arbiter's first step), wall arbiter first */
+            if (!wfirst) {
+                for (int k = 0; k < wcnt; k++) {
+                    if (wall_on_a) wall_contact(k, true, avx, avy, aw, abx, aby, abw);
+                    else wall_contact(k, true, bvx, bvy, bw_, bbx, bby, bbw);
+                }
+            }
+            if (!first) {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (i == 0 || two) {
+                        const float *q = W.isl + (2 + i) * ISL_FIELDS * SCR;
+                        const float jn = q[IF_JN * SCR], jt = q[IF_JT * SCR];
+                        const float jx = nx * jn - ny * jt, jy = ny * jn + nx * jt;
+                        avx -= jx * ma; avy -= jy * ma; aw -= iam * (q[IF_RN1 * SCR] * jn + q[IF_RT1 * SCR] * jt);
+                        bvx += jx * mb; bvy += jy * mb; bw_ += ibm * (q[IF_RN2 * SCR] * jn + q[IF_RT2 * SCR] * jt);
+                    }
+                }
+            }
+            /* cpArbiterApplyImpulse x 10 */
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            for (int it = 0; it < SOLVER_ITERS; it++) {
+                for (int k = 0; k < wcnt; k++) {
+                    if (wall_on_a) wall_contact(k, false, avx, avy, aw, abx, aby, abw);
+                    else wall_contact(k, false, bvx, bvy, bw_, bbx, bby, bbw);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (i == 0 || two) {
+                        float *q = W.isl + (2 + i) * ISL_FIELDS * SCR;
+                        const float rn1 = q[IF_RN1 * SCR], rt1 = q[IF_RT1 * SCR], rn2 = q[IF_RN2 * SCR], rt2 = q[IF_RT2 * SCR];
+                        const float nM = q[IF_NM * SCR], jbO = q[IF_JB * SCR], jnO = q[IF_JN * SCR], jtO = q[IF_JT * SCR];
+                        float vrn = bvx * nx + bvy * ny + bw_ * rn2;
+                        float vrt = bvy * nx - bvx * ny + bw_ * rt2;
+                        float vbn = bbx * nx + bby * ny + bbw * rn2;
+                        vrn -= avx * nx + avy * ny + aw * rn1;
+                        vrt -= avy * nx - avx * ny + aw * rt1;
+                        vbn -= abx * nx + aby * ny + abw * rn1;
+                        const float jbN = fmaxf(jbO + (q[IF_BIAS * SCR] - vbn) * nM, 0.0f);
+                        const float jnN = fmaxf(jnO - (q[IF_BNC * SCR] + vrn) * nM, 0.0f);
+                        const float jtMax = u * jnN;
+                        const float jtN = fminf(fmaxf(jtO - vrt * q[IF_TM * SCR], -jtMax), jtMax);
+                        const float djb = jbN - jbO, djn = jnN - jnO, djt = jtN - jtO;
+                        q[IF_JB * SCR] = jbN; q[IF_JN * SCR] = jnN; q[IF_JT * SCR] = jtN;
+                        const float jx = nx * djn - ny * djt, jy = ny * djn + nx * djt;
+                        bbx += nx * djb * mb; bby += ny * djb * mb; bbw += ibm * rn2 * djb;
+                        bvx += jx * mb; bvy += jy * mb; bw_ += ibm * (rn2 * djn + rt2 * djt);
+                        abx -= nx * djb * ma; aby -= ny * djb * ma; abw -= iam * rn1 * djb;
+                        avx -= jx * ma; avy -= jy * ma; aw -= iam * (rn1 * djn + rt1 * djt);
+                    }
+                }
+            }
+            pa[BF_VX * BODY_FS] = avx; pa[BF_VY * BODY_FS] = avy; pa[BF_W * BODY_FS] = aw;
+            pa[BF_BX * BODY_FS] = abx; pa[BF_BY * BODY_FS] = aby; pa[BF_BW * BODY_FS] = abw;
+            pb[BF_VX * BODY_FS] = bvx; pb[BF_VY * BODY_FS] = bvy; pb[BF_W * BODY_FS] = bw_;
+            pb[BF_BX * BODY_FS] = bbx; pb[BF_BY * BODY_FS] = bby; pb[BF_BW * BODY_FS] = bbw;
+            /* this step's contacts open the arbiter cache of the next step (age 0): wall arbiter, then the pair's */
+            for (int k = 0; k < wcnt; k++) {
+                const float *q = W.isl + k * ISL_FIELDS * SCR;
+                nc_[3 * new_count] = f2u(q[IF_INFO * SCR]); nc_[3 * new_count + 1] = f2u(q[IF_JN * SCR]); nc_[3 * new_count + 2] = f2u(q[IF_JT * SCR]);
+                new_count++;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (i == 0 || two) {
+                    const float *q = W.isl + (2 + i) * ISL_FIELDS * SCR;
+                    nc_[3 * new_count] = (uint32_t)pair | ((uint32_t)m.key[i] << 6); nc_[3 * new_count + 1] = f2u(q[IF_JN * SCR]); nc_[3 * new_count + 2] = f2u(q[IF_JT * SCR]);
+                    new_count++;
+                }
+            }
+            n_contacts += wcnt + m.count;
         }
 
         /* then the untouched arbiters younger than collision_persistence (3) */

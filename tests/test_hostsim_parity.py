@@ -109,8 +109,8 @@ def test_global_offset_shards_agree():
 def test_class_modes_equal_the_general_path(monkeypatch):
     """Every work class of the contact kernel (light: one agent x wall pair; pair: one agent x agent / ball x agent pair;
     multi: several wall pairs) solves its islands on their own.  From identical states the result must be the general
-    path's (HSIM_FORCE_FULL routes every declined env through MODE_FULL) -- bit for bit on the host build, where
-    nothing is contracted -- arbiter cache included."""
+    path's (HSIM_FORCE_FULL routes every declined env through MODE_FULL) -- the same numbers in every state field on the
+    host build, where nothing is contracted -- arbiter cache included."""
     n = 512
     a, b = H.HostSim(n, P.CONFIG, seed=1), H.HostSim(n, P.CONFIG, seed=1)
     a.reset(O.MODE_FULL_RANDOM, seed=1)
@@ -140,5 +140,8 @@ def test_class_modes_equal_the_general_path(monkeypatch):
             seen[k] += int(np.sum((load_a == k) & (cont_a > 0)))
         for i in np.nonzero(load_a >= 0)[0]:
             sa, sb = a.get_state(int(i)), b.get_state(int(i))
-            assert bytes(sa) == bytes(sb), (int(i), int(load_a[i]))
+            for name, _ in type(sa)._fields_:
+                # equal VALUES in every field (a zero tangent impulse of a frictionless goal-line contact may come out as
+                # -0.0 on one path and +0.0 on the other: min / max of two zeros, which the host compiler may order either way)
+                assert np.array_equal(np.array(getattr(sa, name)), np.array(getattr(sb, name))), (int(i), int(load_a[i]), name)
     assert min(seen.values()) > 20, seen   # every class really solved contacts
