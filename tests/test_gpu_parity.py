@@ -190,7 +190,8 @@ def test_chunked_host_step_equals_the_whole_step():
         assert np.array_equal(stack, o_h), t
         assert np.array_equal(r_f, r_h) and np.array_equal(d_f, d_h) and np.array_equal(g_f, g_h)
     assert d_h.sum() == 0 and host.stats()["episodes"] == n  # everybody truncated once, at step 9
-    assert min(seen.values()) > 1000, seen  # (the corner spawns of the first steps are all multi / heavy; light comes later)
+    # (the corner spawns of the first steps are all multi / pair; light comes later; heavy is down to pile-ups of three)
+    assert min(seen[k] for k in ("light", "pair", "multi")) > 1000 and seen["heavy"] > 0, seen
 
 
 def test_ragged_sizes_and_masked_reset():
@@ -340,5 +341,5 @@ def test_class_modes_match_the_general_path_on_the_device():
                 worst[name] = max(worst.get(name, 0.0), err)
     P.record("cuda/class_modes_vs_general_path", {"env_steps_compared": 40 * n, "class_env_steps": seen,
                                                   "worst_violation_ratio": {k: round(v, 3) for k, v in worst.items()}})
-    assert min(seen.values()) > 100, seen
+    assert min(seen[k] for k in ("light", "pair", "multi")) > 100 and seen["heavy"] > 0, seen
     assert max(worst.values()) < 0.7, worst  # observed on the B200: 0.35 (an observation), 0.13 (an angular velocity)

@@ -144,4 +144,6 @@ def test_class_modes_equal_the_general_path(monkeypatch):
                 # equal VALUES in every field (a zero tangent impulse of a frictionless goal-line contact may come out as
                 # -0.0 on one path and +0.0 on the other: min / max of two zeros, which the host compiler may order either way)
                 assert np.array_equal(np.array(getattr(sa, name)), np.array(getattr(sb, name))), (int(i), int(load_a[i]), name)
-    assert min(seen.values()) > 20, seen   # every class really solved contacts
+    # every class with a path of its own really solved contacts (class 1, the general path, is what the other side runs
+    # for everything; on this mix it is down to ~0.1 % of the envs)
+    assert min(seen[k] for k in (0, 2, 3)) > 20, seen
