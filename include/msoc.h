@@ -221,7 +221,8 @@ int msoc_policy_inputs(const float *d_obs, int64_t n_envs, const float *d_shift,
 
 /* Work classes of the last step (instrumentation for tests and bench.py; no counterpart in the reference): how many envs
    the streaming kernel handed to the contact kernel as light (exactly one agent x wall candidate pair), heavy (the
-   general path), pair (exactly one agent x agent / ball x agent pair) and multi (several wall pairs), in this order.
+   general path), pair (exactly one agent x agent / ball x agent pair, at most one wall pair beside it) and multi (several
+   wall pairs), in this order.
    The rest of the envs were contact-free.  Stream-ordered read, then synchronises `stream`. */
 int msoc_last_class_counts(msoc_handle *h, int32_t h_out[4], void *stream);
 

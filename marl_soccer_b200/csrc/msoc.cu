@@ -309,7 +309,7 @@ __device__ __forceinline__ void obs_tile(const Arrays &A, const SimCfg &cfg, flo
                              pair (~27 % in the benchmark mix) write nothing and are appended, one atomic per
                              warp and class, to the list of their work class (step_core.cuh LOAD_*): light
                              (exactly one agent x wall pair, the bulk), pair (exactly one agent x agent or
-                             ball x agent pair), multi (only wall candidates, several), heavy (anything else).
+                             ball x agent pair, at most one agent x wall pair beside it), multi (only wall candidates, several), heavy (anything else).
    msoc_step_contact_kernel  every warp of a persistent grid pulls batches of listed envs of ONE class -- heavy
                              batches first, then multi, pair, light: longest first -- and every thread steps one
                              env in the mode of its class: the register-only single-body solver (light), islands
